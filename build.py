@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""Build libdtcwt_b200.so (sm_100a) in-tree with nvcc.  Usage: python build.py [--force] [--ptxas-v]"""
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(ROOT, "dtcwt_b200", "csrc")
+OUT = os.path.join(ROOT, "dtcwt_b200", "libdtcwt_b200.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+
+
+def _nvcc():
+    for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.isfile(c):
+            return c
+    return None
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def up_to_date():
+    if not os.path.isfile(OUT):
+        return False
+    deps = glob.glob(os.path.join(CSRC, "*")) + [os.path.join(ROOT, "include", "dtcwt_b200.h")]
+    return all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps)
+
+
+def build(force=False, verbose=False, extra=()):
+    if not force and up_to_date():
+        return OUT
+    nvcc = _nvcc()
+    if nvcc is None:
+        if os.path.isfile(OUT):
+            return OUT      # GPU box without a toolkit on PATH: use the library shipped in the snapshot
+        raise RuntimeError("nvcc not found and %s does not exist" % OUT)
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-I", os.path.join(ROOT, "include"), "-o", OUT] + sources()
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd, cwd=ROOT)
+    return OUT
+
+
+if __name__ == "__main__":
+    extra = ["-Xptxas", "-v"] if "--ptxas-v" in sys.argv else []
+    print(build(force="--force" in sys.argv or bool(extra), verbose=True, extra=extra))

@@ -1,0 +1,108 @@
+"""ctypes binding of ``libdtcwt_b200.so`` (the C ABI declared in ``include/dtcwt_b200.h``).
+
+There is exactly one compute path: the CUDA library.  If it has not been built,
+or no CUDA device is present, the first call raises ``RuntimeError`` -- there is
+no CPU fallback.  (``_install_emulator_for_tests`` exists so that the CPU
+test-suite can run the host logic against ``tests/emu``'s host build of the same
+kernel bodies; nothing in the package calls it.)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdtcwt_b200.so")
+
+_LIB = None
+_EMULATED = False
+
+_P, _I, _L, _D = c_void_p, c_int, c_int64, c_double
+_TAPS = ctypes.POINTER(c_double)
+
+# name (without _f32/_f64 suffix) -> argtypes; keep in step with include/dtcwt_b200.h
+_TYPED = {
+    "colfilter": [_P, _P, _L, _L, _L, _I, _I, _TAPS, _I, _I, _P],
+    "coldfilt": [_P, _P, _L, _L, _L, _I, _I, _TAPS, _TAPS, _I, _I, _P],
+    "colifilt": [_P, _P, _L, _L, _L, _I, _TAPS, _TAPS, _I, _I, _P],
+    "q2c": [_P, _P, _L, _L, _L, _L, _L, _L, _L, _I, _I, _P],
+    "c2q": [_P, _P, _L, _L, _L, _L, _L, _L, _L, _I, _I, _D, _D, _P],
+    "pack1d": [_P, _P, _L, _L, _L, _P],
+    "unpack1d": [_P, _P, _L, _L, _L, _D, _P],
+    "cube2c": [_P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _P],
+    "c2cube": [_P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _P],
+}
+_F32_ONLY = {}
+
+EXPORTS = (["dtcwt_b200_version", "dtcwt_b200_error_string", "dtcwt_b200_is_device_build"]
+           + ["dtcwt_b200_%s_%s" % (n, s) for n in _TYPED for s in ("f32", "f64")]
+           + ["dtcwt_b200_%s_f32" % n for n in _F32_ONLY])
+
+
+def _bind(path):
+    lib = ctypes.CDLL(path)
+    lib.dtcwt_b200_version.restype = c_int
+    lib.dtcwt_b200_version.argtypes = []
+    lib.dtcwt_b200_is_device_build.restype = c_int
+    lib.dtcwt_b200_is_device_build.argtypes = []
+    lib.dtcwt_b200_error_string.restype = c_char_p
+    lib.dtcwt_b200_error_string.argtypes = [c_int]
+    for name, args in _TYPED.items():
+        for suf in ("f32", "f64"):
+            fn = getattr(lib, "dtcwt_b200_%s_%s" % (name, suf))
+            fn.restype = c_int
+            fn.argtypes = args
+    for name, args in _F32_ONLY.items():
+        fn = getattr(lib, "dtcwt_b200_%s_f32" % name)
+        fn.restype = c_int
+        fn.argtypes = args
+    return lib
+
+
+def lib():
+    """The loaded CUDA library; raises RuntimeError when it cannot be used."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                "dtcwt_b200: %s has not been built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `python build.py`); there is no CPU fallback" % LIB_PATH)
+        loaded = _bind(LIB_PATH)
+        if not loaded.dtcwt_b200_is_device_build():
+            raise RuntimeError("dtcwt_b200: %s is not a device build" % LIB_PATH)
+        _LIB = loaded
+    return _LIB
+
+
+def emulated():
+    return _EMULATED
+
+
+def device_type():
+    """Device type the host layer places tensors on ('cuda'; 'cpu' only under the test emulator)."""
+    return "cpu" if _EMULATED else "cuda"
+
+
+def _install_emulator_for_tests(path):
+    """TEST SEAM: route calls to tests/emu's host build of the kernel bodies."""
+    global _LIB, _EMULATED
+    if path is None:
+        _LIB, _EMULATED = None, False
+        return
+    loaded = _bind(path)
+    if loaded.dtcwt_b200_is_device_build():
+        raise RuntimeError("refusing to install a device build as the emulator")
+    _LIB, _EMULATED = loaded, True
+
+
+def check(code):
+    if code != 0:
+        msg = lib().dtcwt_b200_error_string(code).decode()
+        if code < 0:
+            raise ValueError(msg)
+        raise RuntimeError("CUDA error %d: %s" % (code, msg))
+
+
+def call(name, dtype_suffix, *args):
+    check(getattr(lib(), "dtcwt_b200_%s_%s" % (name, dtype_suffix))(*args))

@@ -1,0 +1,222 @@
+"""Thin tensor-level wrappers over the C ABI: shapes in, launches out.
+
+Every function takes C-contiguous ``torch.Tensor`` arguments that already live on
+the compute device, describes them to the library as ``[outer][len][inner]``
+views (see ``include/dtcwt_b200.h``) and returns freshly allocated outputs.
+PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_SUFFIX = {torch.float32: "f32", torch.float64: "f64"}
+_COMPLEX = {torch.float32: torch.complex64, torch.float64: torch.complex128}
+_REAL = {torch.complex64: torch.float32, torch.complex128: torch.float64}
+
+
+# ----------------------------------------------------------------------------- coercion
+def as_real_tensor(X, name="X"):
+    """Array-like / tensor -> contiguous float32/float64 tensor on the compute device.
+
+    dtype rules follow the reference's ``asfarray`` (utils.py:98-105): float32 and
+    float64 are kept, everything else becomes float64 (float16/bfloat16 -> float32).
+    """
+    if not isinstance(X, torch.Tensor):
+        X = np.asarray(X)
+        if X.dtype not in (np.float32, np.float64):
+            if np.issubdtype(X.dtype, np.complexfloating):
+                raise ValueError("%s must be real" % name)
+            X = X.astype(np.float64)
+        X = torch.from_numpy(np.ascontiguousarray(X))
+    if X.is_complex():
+        raise ValueError("%s must be real" % name)
+    if X.dtype in (torch.float16, torch.bfloat16):
+        X = X.float()
+    elif X.dtype not in (torch.float32, torch.float64):
+        X = X.double()
+    return to_device(X).contiguous()
+
+
+def as_complex_tensor(Z, real_dtype=None):
+    if not isinstance(Z, torch.Tensor):
+        Z = np.asarray(Z)
+        if not np.issubdtype(Z.dtype, np.complexfloating):
+            Z = Z.astype(np.complex64 if Z.dtype == np.float32 else np.complex128)
+        Z = torch.from_numpy(Z)   # may be non-contiguous; callers re-layout
+    if not Z.is_complex():
+        Z = Z.to(_COMPLEX.get(Z.dtype, torch.complex128))
+    if real_dtype is not None and _REAL[Z.dtype] != real_dtype:
+        Z = Z.to(_COMPLEX[real_dtype])
+    return to_device(Z)
+
+
+def to_device(t):
+    kind = _lib.device_type()
+    if t.device.type == kind:
+        return t
+    if kind == "cuda":
+        if not torch.cuda.is_available():
+            raise RuntimeError("dtcwt_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        return t.cuda(non_blocking=False)
+    return t.cpu()
+
+
+def complex_dtype(real_dtype):
+    return _COMPLEX[real_dtype]
+
+
+def _stream(t):
+    if t.device.type == "cuda":
+        return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    return ctypes.c_void_p(0)
+
+
+class _on_device(object):
+    """Make the tensor's device current for the duration of a launch."""
+
+    def __init__(self, t):
+        self.ctx = torch.cuda.device(t.device) if t.device.type == "cuda" else None
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+
+
+def _taps(h):
+    h = np.ascontiguousarray(np.asarray(h, dtype=np.float64).reshape(-1))
+    return h, h.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(h.shape[0])
+
+
+def _view(shape, axis):
+    outer = int(np.prod(shape[:axis], dtype=np.int64))
+    inner = int(np.prod(shape[axis + 1:], dtype=np.int64))
+    return outer, int(shape[axis]), inner
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+# ----------------------------------------------------------------------------- filters
+def colfilter(x, h, axis, pad=(0, 0), out=None, accumulate=False):
+    hk, hp, m = _taps(h)
+    outer, n, inner = _view(x.shape, axis)
+    L = n + pad[0] + pad[1]
+    shape = list(x.shape)
+    shape[axis] = L if m % 2 else L + 1
+    y = _out(x, shape, out, accumulate)
+    with _on_device(x):
+        _lib.call("colfilter", _SUFFIX[x.dtype], _ptr(x), _ptr(y), outer, n, inner, pad[0], pad[1],
+                  hp, m, int(accumulate), _stream(x))
+    return y
+
+
+def coldfilt(x, ha, hb, axis, pad=(0, 0), out=None, accumulate=False):
+    ka, pa, m = _taps(ha)
+    kb, pb, mb = _taps(hb)
+    outer, n, inner = _view(x.shape, axis)
+    L = n + pad[0] + pad[1]
+    shape = list(x.shape)
+    shape[axis] = L // 2
+    y = _out(x, shape, out, accumulate)
+    with _on_device(x):
+        _lib.call("coldfilt", _SUFFIX[x.dtype], _ptr(x), _ptr(y), outer, n, inner, pad[0], pad[1],
+                  pa, pb, m, int(accumulate), _stream(x))
+    return y
+
+
+def colifilt(x, ha, hb, axis, crop=0, out=None, accumulate=False):
+    ka, pa, m = _taps(ha)
+    kb, pb, mb = _taps(hb)
+    outer, n, inner = _view(x.shape, axis)
+    shape = list(x.shape)
+    shape[axis] = 2 * n - 2 * crop
+    y = _out(x, shape, out, accumulate)
+    with _on_device(x):
+        _lib.call("colifilt", _SUFFIX[x.dtype], _ptr(x), _ptr(y), outer, n, inner, crop,
+                  pa, pb, m, int(accumulate), _stream(x))
+    return y
+
+
+def _out(x, shape, out, accumulate):
+    if out is None:
+        if accumulate:
+            raise ValueError("accumulate needs an output tensor")
+        return torch.empty(shape, dtype=x.dtype, device=x.device)
+    if list(out.shape) != list(shape) or out.dtype != x.dtype or not out.is_contiguous():
+        raise ValueError("output tensor has the wrong shape/dtype: %s vs %s" % (list(out.shape), list(shape)))
+    return out
+
+
+# ----------------------------------------------------------------------------- 2-D packing
+def new_highpass(n, bands, spatial, real_dtype, device):
+    """Planar sub-band storage [n][bands][*spatial] (complex)."""
+    return torch.empty((n, bands) + tuple(spatial), dtype=_COMPLEX[real_dtype], device=device)
+
+
+def q2c(y, z, band0, band1):
+    """y real [n][2h][2w] -> bands band0/band1 of planar z [n][6][h][w]."""
+    n, h2, w2 = y.shape
+    h, w = h2 // 2, w2 // 2
+    assert z.shape[0] == n and tuple(z.shape[2:]) == (h, w) and z.is_contiguous()
+    with _on_device(y):
+        _lib.call("q2c", _SUFFIX[y.dtype], _ptr(y), _ptr(z), n, h, w,
+                  z.stride(0), z.stride(1), z.stride(2), z.stride(3), band0, band1, _stream(y))
+
+
+def c2q(z, band0, band1, gain0, gain1):
+    """bands band0/band1 of planar z [n][6][h][w] -> real [n][2h][2w]."""
+    n, _, h, w = z.shape
+    y = torch.empty((n, 2 * h, 2 * w), dtype=_REAL[z.dtype], device=z.device)
+    with _on_device(z):
+        _lib.call("c2q", _SUFFIX[y.dtype], _ptr(z), _ptr(y), n, h, w,
+                  z.stride(0), z.stride(1), z.stride(2), z.stride(3), band0, band1,
+                  float(gain0), float(gain1), _stream(z))
+    return y
+
+
+# ----------------------------------------------------------------------------- 1-D packing
+def pack1d(hi):
+    """real [2k][c] -> complex [k][c]: even rows real part, odd rows imaginary part."""
+    k2, c = hi.shape
+    z = torch.empty((k2 // 2, c), dtype=_COMPLEX[hi.dtype], device=hi.device)
+    with _on_device(hi):
+        _lib.call("pack1d", _SUFFIX[hi.dtype], _ptr(hi), _ptr(z), 1, k2 // 2, c, _stream(hi))
+    return z
+
+
+def unpack1d(z, gain):
+    k, c = z.shape
+    hi = torch.empty((2 * k, c), dtype=_REAL[z.dtype], device=z.device)
+    with _on_device(z):
+        _lib.call("unpack1d", _SUFFIX[hi.dtype], _ptr(z), _ptr(hi), 1, k, c, float(gain), _stream(z))
+    return hi
+
+
+# ----------------------------------------------------------------------------- 3-D packing
+def cube2c(y, z, chan0):
+    """y real [n][2a][2b][2c] -> channels chan0..chan0+3 of planar z [n][28][a][b][c]."""
+    n = y.shape[0]
+    a, b, c = (s // 2 for s in y.shape[1:])
+    assert tuple(z.shape[2:]) == (a, b, c) and z.is_contiguous()
+    with _on_device(y):
+        _lib.call("cube2c", _SUFFIX[y.dtype], _ptr(y), _ptr(z), n, a, b, c,
+                  z.stride(0), z.stride(1), z.stride(2), z.stride(3), z.stride(4), chan0, _stream(y))
+
+
+def c2cube(z, chan0):
+    n, _, a, b, c = z.shape
+    y = torch.empty((n, 2 * a, 2 * b, 2 * c), dtype=_REAL[z.dtype], device=z.device)
+    with _on_device(z):
+        _lib.call("c2cube", _SUFFIX[y.dtype], _ptr(z), _ptr(y), n, a, b, c,
+                  z.stride(0), z.stride(1), z.stride(2), z.stride(3), z.stride(4), chan0, _stream(z))
+    return y

@@ -1,0 +1,44 @@
+// Device build of libdtcwt_b200.so: nvcc -gencode arch=compute_100a,code=sm_100a
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "generic_kernels.cuh"
+
+namespace dtcwt {
+
+// One thread per output element; gid spans blockIdx.x (2^31-1 blocks of 256 threads
+// covers 5e11 elements).  Used by every generic kernel.
+template <class Elem>
+__global__ void __launch_bounds__(256) generic_1d_kernel(const typename Elem::Args a, const int64_t total) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < total) Elem::run(a, gid);
+}
+
+template <class Elem>
+static int launch_1d(const typename Elem::Args& a, void* stream) {
+    const int64_t total = Elem::total(a);
+    if (total <= 0) return DTCWT_B200_OK;
+    const int threads = 256;
+    const int64_t blocks = (total + threads - 1) / threads;
+    if (blocks > 0x7fffffffLL) return DTCWT_B200_EUNSUPPORTED;
+    generic_1d_kernel<Elem><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(a, total);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace dtcwt
+
+#include "abi_generic.inl"
+
+extern "C" {
+
+int dtcwt_b200_is_device_build(void) { return 1; }
+
+const char* dtcwt_b200_error_string(int code) {
+    if (code == DTCWT_B200_OK) return "ok";
+    if (code == DTCWT_B200_EINVAL) return "dtcwt_b200: invalid argument (shape, tap count or NULL pointer)";
+    if (code == DTCWT_B200_EUNSUPPORTED) return "dtcwt_b200: request not supported by this build";
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "dtcwt_b200: unknown error";
+}
+
+}  // extern "C"

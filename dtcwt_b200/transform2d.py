@@ -1,0 +1,277 @@
+"""2-D DT-CWT on the GPU -- drop-in for ``dtcwt.numpy.Transform2d``.
+
+Mirrors the reference class (``dtcwt/numpy/transform2d.py:15-295``): same
+constructor, ``forward(X, nlevels=3, include_scale=False)`` and
+``inverse(pyramid, gain_mask=None)``, same padding rules (odd sizes repeat the
+last row/column, :86-94; a level whose input is not a multiple of 4 is
+edge-extended by one sample per side, :134-140, and cropped again by the
+inverse, :263-271), same exceptions.
+
+Batches: ``forward_channels`` / ``inverse_channels`` (names from the reference's
+TensorFlow backend, ``dtcwt/tf/transform2d.py:179,422``) take ``[N][H][W]``.
+Every image of a batch is independent, so a batch is also the unit that is
+sharded across GPUs (see ``dtcwt_b200.parallel``).
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import torch
+
+from . import _ops
+from .coeffs import biort as _biort, qshift as _qshift
+from .common import Pyramid
+from .defaults import DEFAULT_BIORT, DEFAULT_QSHIFT
+
+__all__ = ["Transform2d"]
+
+# (band0, band1) written by q2c of the three highpass images, reference transform2d.py:122-127:
+#   vertical-highpass x horizontal-lowpass -> bands 0,5 ; lowpass x highpass -> 2,3 ; high x high -> 1,4
+_BANDS_HL, _BANDS_LH, _BANDS_HH = (0, 5), (2, 3), (1, 4)
+
+
+def _vec(h):
+    return np.asarray(h, dtype=np.float64).reshape(-1)
+
+
+class Transform2d(object):
+    """*biort* / *qshift* are family names (``dtcwt_b200.coeffs``) or tuples of tap vectors:
+    ``(h0o, g0o, h1o, g1o[, h2o, g2o])`` and ``(h0a, h0b, g0a, g0b, h1a, h1b, g1a, g1b[, h2a, h2b, g2a, g2b])``.
+    """
+
+    def __init__(self, biort=DEFAULT_BIORT, qshift=DEFAULT_QSHIFT):
+        try:
+            self.biort = _biort(biort)
+        except TypeError:
+            self.biort = biort
+        try:
+            self.qshift = _qshift(qshift)
+        except TypeError:
+            self.qshift = qshift
+
+    # ------------------------------------------------------------------ tap bookkeeping
+    def _taps(self):
+        if len(self.biort) == 4:
+            h0o, g0o, h1o, g1o = self.biort
+            h2o = g2o = None
+        elif len(self.biort) == 6:
+            h0o, g0o, h1o, g1o, h2o, g2o = self.biort
+        else:
+            raise ValueError("Biort wavelet must have 6 or 4 components.")
+        if len(self.qshift) == 8:
+            h0a, h0b, g0a, g0b, h1a, h1b, g1a, g1b = self.qshift
+            h2a = h2b = g2a = g2b = None
+        elif len(self.qshift) == 12:
+            h0a, h0b, g0a, g0b, h1a, h1b, g1a, g1b, h2a, h2b, g2a, g2b = self.qshift
+        else:
+            raise ValueError("Qshift wavelet must have 12 or 8 components.")
+        v = lambda h: None if h is None else _vec(h)  # noqa: E731
+        return dict(h0o=v(h0o), g0o=v(g0o), h1o=v(h1o), g1o=v(g1o), h2o=v(h2o), g2o=v(g2o),
+                    h0a=v(h0a), h0b=v(h0b), g0a=v(g0a), g0b=v(g0b), h1a=v(h1a), h1b=v(h1b),
+                    g1a=v(g1a), g1b=v(g1b), h2a=v(h2a), h2b=v(h2b), g2a=v(g2a), g2b=v(g2b))
+
+    # ------------------------------------------------------------------ public API
+    def forward(self, X, nlevels=3, include_scale=False):
+        """*nlevels*-level transform of one 2-D image; returns a :class:`Pyramid`."""
+        t = self._taps()
+        X = _ops.as_real_tensor(X)
+        if X.dim() >= 3:
+            raise ValueError("The entered image is {0}, which is invalid for the 2D transform. "
+                             "Use forward_channels for a batch.".format("x".join(str(s) for s in X.shape)))
+        while X.dim() < 2:
+            X = X.unsqueeze(0)
+        return self._unbatch(self._forward_n(X.unsqueeze(0), t, nlevels, include_scale))
+
+    def inverse(self, pyramid, gain_mask=None):
+        """Reconstruct from a Pyramid-like object (ours, the reference's, or any object with
+        ``lowpass`` / ``highpasses``); *gain_mask* is ``(6, nlevels)`` (reference :214-217)."""
+        t = self._taps()
+        Yl, Yh = self._pyramid_tensors(pyramid)
+        batched = Yl.dim() == 3
+        if not batched:
+            Yl = Yl.unsqueeze(0)
+        Z = self._inverse_n(Yl, Yh, t, gain_mask)
+        return Z if batched else Z[0]
+
+    def forward_channels(self, X, data_format="nhw", nlevels=3, include_scale=False):
+        """Batched forward: X is ``[N][H][W]`` (``data_format='nhw'``) or ``[N][C][H][W]`` ('nchw')."""
+        t = self._taps()
+        X = _ops.as_real_tensor(X)
+        data_format = data_format.lower()
+        if data_format == "nhw" and X.dim() == 3:
+            return self._forward_n(X, t, nlevels, include_scale)
+        if data_format == "nchw" and X.dim() == 4:
+            n, c = X.shape[:2]
+            p = self._forward_n(X.reshape((n * c,) + tuple(X.shape[2:])), t, nlevels, include_scale)
+            unf = lambda a: a.reshape((n, c) + tuple(a.shape[1:]))  # noqa: E731
+            return Pyramid(unf(p.lowpass_t), tuple(unf(h) for h in p.highpasses_t),
+                           None if p.scales_t is None else tuple(unf(s) for s in p.scales_t))
+        raise ValueError("data_format must be 'nhw' (3-D input) or 'nchw' (4-D input)")
+
+    def inverse_channels(self, pyramid, data_format="nhw", gain_mask=None):
+        t = self._taps()
+        data_format = data_format.lower()
+        Yl, Yh = self._pyramid_tensors(pyramid, batch_dims=2 if data_format == "nchw" else 1)
+        if data_format == "nhw" and Yl.dim() == 3:
+            return self._inverse_n(Yl, Yh, t, gain_mask)
+        if data_format == "nchw" and Yl.dim() == 4:
+            n, c = Yl.shape[:2]
+            Z = self._inverse_n(Yl.reshape((n * c,) + tuple(Yl.shape[2:])), Yh, t, gain_mask)
+            return Z.reshape((n, c) + tuple(Z.shape[1:]))
+        raise ValueError("data_format must be 'nhw' (3-D lowpass) or 'nchw' (4-D lowpass)")
+
+    # ------------------------------------------------------------------ pyramid plumbing
+    @staticmethod
+    def _unbatch(p):
+        hp = tuple(h[0] for h in p.highpasses_t)
+        sc = None if p.scales_t is None else tuple(s[0] for s in p.scales_t)
+        return Pyramid(p.lowpass_t[0], hp, sc)
+
+    @staticmethod
+    def _pyramid_tensors(pyramid, batch_dims=None):
+        """-> (lowpass [N..][h][w] real, [planar highpass [M][6][h][w] complex per level])."""
+        lo = getattr(pyramid, "lowpass_t", None)
+        hs = getattr(pyramid, "highpasses_t", None)
+        if lo is None or hs is None:
+            lo, hs = pyramid.lowpass, pyramid.highpasses
+        lo = _ops.as_real_tensor(lo, "lowpass")
+        planar = []
+        for h in hs:
+            h = _ops.as_complex_tensor(h, lo.dtype)
+            if h.shape[-1] != 6:
+                raise ValueError("highpass arrays must have 6 sub-bands on their last axis")
+            if h.dim() == 3:
+                h = h.unsqueeze(0)
+            h = h.reshape((-1,) + tuple(h.shape[-3:]))          # [M][h][w][6]
+            planar.append(h.permute(0, 3, 1, 2).contiguous())   # no copy when already planar
+        return lo, planar
+
+    # ------------------------------------------------------------------ forward
+    def _forward_n(self, X, t, nlevels, include_scale):
+        N, H, W = X.shape
+        if H < 1 or W < 1:
+            raise ValueError("empty image")
+        ph, pw = H % 2, W % 2          # odd size: repeat last row / column (reference :86-94)
+        if nlevels == 0:
+            if ph or pw:
+                X = torch.nn.functional.pad(X.unsqueeze(1), (0, pw, 0, ph), mode="replicate").squeeze(1)
+            return Pyramid(X, (), ()) if include_scale else Pyramid(X, ())
+        if t["h0o"].shape[0] % 2 == 0 or t["h1o"].shape[0] % 2 == 0:
+            raise ValueError("even-length biorthogonal filters are not supported by the 2-D transform")
+        Yh, Ysc = [], []
+        LoLo, yh = self._fwd_level1(X, t, ph, pw)
+        Yh.append(yh)
+        Ysc.append(LoLo)
+        for _ in range(1, nlevels):
+            LoLo, yh = self._fwd_levelq(LoLo, t)
+            Yh.append(yh)
+            Ysc.append(LoLo)
+        if ph or pw:
+            logging.warning("The image entered is now a %dx%d NOT a %dx%d.", H + ph, W + pw, H, W)
+            logging.warning("The %s been duplicated, prior to decomposition.",
+                            {(1, 1): "bottom row and rightmost column have", (1, 0): "bottom row has",
+                             (0, 1): "rightmost column has"}[(ph, pw)])
+        views = tuple(h.permute(0, 2, 3, 1) for h in Yh)         # [N][h][w][6] views of planar storage
+        return Pyramid(LoLo, views, tuple(Ysc)) if include_scale else Pyramid(LoLo, views)
+
+    def _fwd_level1(self, X, t, ph, pw):
+        """Level 1 (reference :112-130): undecimated biort filters, vertical axis first."""
+        N = X.shape[0]
+        Lo = _ops.colfilter(X, t["h0o"], 1, (0, ph))
+        Hi = _ops.colfilter(X, t["h1o"], 1, (0, ph))
+        LoLo = _ops.colfilter(Lo, t["h0o"], 2, (0, pw))
+        yh = _ops.new_highpass(N, 6, (LoLo.shape[1] // 2, LoLo.shape[2] // 2), X.dtype, X.device)
+        _ops.q2c(_ops.colfilter(Hi, t["h0o"], 2, (0, pw)), yh, *_BANDS_HL)
+        _ops.q2c(_ops.colfilter(Lo, t["h1o"], 2, (0, pw)), yh, *_BANDS_LH)
+        if t["h2o"] is not None:
+            Ba = _ops.colfilter(X, t["h2o"], 1, (0, ph))
+            _ops.q2c(_ops.colfilter(Ba, t["h2o"], 2, (0, pw)), yh, *_BANDS_HH)
+        else:
+            _ops.q2c(_ops.colfilter(Hi, t["h1o"], 2, (0, pw)), yh, *_BANDS_HH)
+        return LoLo, yh
+
+    def _fwd_levelq(self, LoLo, t):
+        """Level >= 2 (reference :132-160): decimating q-shift pairs."""
+        N, r, c = LoLo.shape
+        pr = (1, 1) if r % 4 else (0, 0)
+        pc = (1, 1) if c % 4 else (0, 0)
+        Lo = _ops.coldfilt(LoLo, t["h0b"], t["h0a"], 1, pr)
+        Hi = _ops.coldfilt(LoLo, t["h1b"], t["h1a"], 1, pr)
+        out = _ops.coldfilt(Lo, t["h0b"], t["h0a"], 2, pc)
+        yh = _ops.new_highpass(N, 6, (out.shape[1] // 2, out.shape[2] // 2), LoLo.dtype, LoLo.device)
+        _ops.q2c(_ops.coldfilt(Hi, t["h0b"], t["h0a"], 2, pc), yh, *_BANDS_HL)
+        _ops.q2c(_ops.coldfilt(Lo, t["h1b"], t["h1a"], 2, pc), yh, *_BANDS_LH)
+        if t["h2a"] is not None:
+            Ba = _ops.coldfilt(LoLo, t["h2b"], t["h2a"], 1, pr)
+            _ops.q2c(_ops.coldfilt(Ba, t["h2b"], t["h2a"], 2, pc), yh, *_BANDS_HH)
+        else:
+            _ops.q2c(_ops.coldfilt(Hi, t["h1b"], t["h1a"], 2, pc), yh, *_BANDS_HH)
+        return out, yh
+
+    # ------------------------------------------------------------------ inverse
+    def _inverse_n(self, Z, Yh, t, gain_mask):
+        a = len(Yh)
+        gm = np.ones((6, a)) if gain_mask is None else np.array(gain_mask, dtype=np.float64)
+        if gm.shape != (6, a):
+            raise ValueError("gain_mask must have shape (6, %d)" % a)
+        N = Z.shape[0]
+        for h in Yh:
+            if h.shape[0] != N:
+                raise ValueError("lowpass and highpass batch sizes differ")
+        for lev in range(a, 1, -1):                      # reference :240-273
+            want = (2 * Yh[lev - 2].shape[2], 2 * Yh[lev - 2].shape[3])
+            Z = self._inv_levelq(Z, Yh[lev - 1], t, gm[:, lev - 1], want)
+        if a >= 1:                                        # reference :275-293
+            Z = self._inv_level1(Z, Yh[0], t, gm[:, 0])
+        return Z
+
+    @staticmethod
+    def _check_lowpass(Z, yh):
+        if (Z.shape[1], Z.shape[2]) != (2 * yh.shape[2], 2 * yh.shape[3]):
+            raise ValueError("Sizes of highpasses are not valid for DTWAVEIFM2")
+
+    def _inv_levelq(self, Z, yh, t, g, want):
+        self._check_lowpass(Z, yh)
+        crops = []
+        for have, need in zip((2 * Z.shape[1], 2 * Z.shape[2]), want):
+            if have == need:
+                crops.append(0)
+            elif have - 2 == need:
+                crops.append(1)      # this level's input had been edge-extended (reference :263-268)
+            else:
+                raise ValueError("Sizes of highpasses are not valid for DTWAVEIFM2")
+        cr, cc = crops
+        lh = _ops.c2q(yh, _BANDS_HL[0], _BANDS_HL[1], g[0], g[5])
+        hl = _ops.c2q(yh, _BANDS_LH[0], _BANDS_LH[1], g[2], g[3])
+        hh = _ops.c2q(yh, _BANDS_HH[0], _BANDS_HH[1], g[1], g[4])
+        y1 = _ops.colifilt(Z, t["g0b"], t["g0a"], 1, cr)
+        _ops.colifilt(lh, t["g1b"], t["g1a"], 1, cr, out=y1, accumulate=True)
+        y2 = _ops.colifilt(hl, t["g0b"], t["g0a"], 1, cr)
+        if t["g2a"] is not None:
+            y3 = _ops.colifilt(hh, t["g2b"], t["g2a"], 1, cr)
+        else:
+            _ops.colifilt(hh, t["g1b"], t["g1a"], 1, cr, out=y2, accumulate=True)
+        out = _ops.colifilt(y1, t["g0b"], t["g0a"], 2, cc)
+        _ops.colifilt(y2, t["g1b"], t["g1a"], 2, cc, out=out, accumulate=True)
+        if t["g2a"] is not None:
+            _ops.colifilt(y3, t["g2b"], t["g2a"], 2, cc, out=out, accumulate=True)
+        return out
+
+    def _inv_level1(self, Z, yh, t, g):
+        self._check_lowpass(Z, yh)
+        lh = _ops.c2q(yh, _BANDS_HL[0], _BANDS_HL[1], g[0], g[5])
+        hl = _ops.c2q(yh, _BANDS_LH[0], _BANDS_LH[1], g[2], g[3])
+        hh = _ops.c2q(yh, _BANDS_HH[0], _BANDS_HH[1], g[1], g[4])
+        y1 = _ops.colfilter(Z, t["g0o"], 1)
+        _ops.colfilter(lh, t["g1o"], 1, out=y1, accumulate=True)
+        y2 = _ops.colfilter(hl, t["g0o"], 1)
+        if t["g2o"] is not None:
+            y3 = _ops.colfilter(hh, t["g2o"], 1)
+        else:
+            _ops.colfilter(hh, t["g1o"], 1, out=y2, accumulate=True)
+        out = _ops.colfilter(y1, t["g0o"], 2)
+        _ops.colfilter(y2, t["g1o"], 2, out=out, accumulate=True)
+        if t["g2o"] is not None:
+            _ops.colfilter(y3, t["g2o"], 2, out=out, accumulate=True)
+        return out

@@ -1,0 +1,138 @@
+/*
+ * dtcwt_b200 -- C ABI of the Blackwell (sm_100a) DT-CWT hot path.
+ *
+ * This is the drop-in boundary: everything the host layer (dtcwt_b200/*.py, the
+ * mirror of the reference's dtcwt.numpy backend) needs from the device goes
+ * through the entry points below.  The reference (rjw57/dtcwt) is pure Python
+ * and has no FFI of its own; each entry point therefore cites the reference
+ * FUNCTION it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers (e.g. torch.Tensor.data_ptr()); tap
+ *    pointers (const double* h...) are HOST pointers to float64 taps, which are
+ *    rounded to the data type inside the call (reference lowlevel.py:33) and
+ *    passed to the kernels by value -- the library keeps no global state, does
+ *    not allocate, and is re-entrant across streams and devices.
+ *  - `stream` is a cudaStream_t (NULL = legacy default stream).  Launches are
+ *    asynchronous; nothing here synchronises.
+ *  - A real array filtered along one axis is described as a C-contiguous
+ *    [outer][len][inner] view: e.g. an image batch [N][H][W] is (N, H, W) for
+ *    the vertical axis and (N*H, W, 1) for the horizontal one; a volume batch
+ *    [N][D0][D1][D2] filtered along D1 is (N*D0, D1, D2).
+ *  - `pad_lo`/`pad_hi`: the input is treated as if `pad_lo` copies of its first
+ *    sample and `pad_hi` copies of its last sample had been attached along the
+ *    filtered axis (the reference's odd-size / not-divisible-by-4 extension,
+ *    transform2d.py:86-94,134-140; transform3d.py:322-335) -- no copy is made.
+ *  - `crop`: the first and last `crop` output samples along the filtered axis
+ *    are not produced (reference transform2d.py:263-268, transform3d.py:505-524).
+ *  - `accumulate` != 0 adds the result to `y` instead of overwriting it (the
+ *    inverse transforms sum two or three filtered arrays).
+ *  - complex arrays are interleaved (re, im) pairs of the real type; complex
+ *    strides are in COMPLEX elements.
+ *  - Return value: 0 on success, < 0 for an argument error (DTCWT_B200_E*),
+ *    > 0 a cudaError_t.  dtcwt_b200_error_string() describes either.
+ */
+#ifndef DTCWT_B200_H
+#define DTCWT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DTCWT_B200_VERSION 100          /* 0.1.0 */
+#define DTCWT_B200_MAX_TAPS 32          /* longest filter accepted (qshift_32) */
+
+#define DTCWT_B200_OK 0
+#define DTCWT_B200_EINVAL (-1)          /* bad shape / tap count / NULL pointer */
+#define DTCWT_B200_EUNSUPPORTED (-2)    /* valid request this build has no kernel for */
+
+int dtcwt_b200_version(void);
+const char *dtcwt_b200_error_string(int code);
+/* 1 when the library was built from the device sources (nvcc, sm_100a); the
+ * host-side kernel-logic emulator used by the CPU test-suite reports 0. */
+int dtcwt_b200_is_device_build(void);
+
+/* ---- the three 1-D filters -------------------------------------------------
+ * replaces dtcwt/numpy/lowlevel.py: colfilter (:47-80), coldfilt (:82-154),
+ * colifilt (:156-260).  L = len + pad_lo + pad_hi is the logical input length.
+ *   colfilter: y is [outer][L or L+1 (m even)][inner]
+ *   coldfilt : needs L % 4 == 0, m even;  y is [outer][L/2][inner]
+ *   colifilt : needs len % 2 == 0, m even; y is [outer][2*len - 2*crop][inner]
+ */
+int dtcwt_b200_colfilter_f32(const float *x, float *y, int64_t outer, int64_t len, int64_t inner,
+                             int pad_lo, int pad_hi, const double *h, int m,
+                             int accumulate, void *stream);
+int dtcwt_b200_colfilter_f64(const double *x, double *y, int64_t outer, int64_t len, int64_t inner,
+                             int pad_lo, int pad_hi, const double *h, int m,
+                             int accumulate, void *stream);
+int dtcwt_b200_coldfilt_f32(const float *x, float *y, int64_t outer, int64_t len, int64_t inner,
+                            int pad_lo, int pad_hi, const double *ha, const double *hb, int m,
+                            int accumulate, void *stream);
+int dtcwt_b200_coldfilt_f64(const double *x, double *y, int64_t outer, int64_t len, int64_t inner,
+                            int pad_lo, int pad_hi, const double *ha, const double *hb, int m,
+                            int accumulate, void *stream);
+int dtcwt_b200_colifilt_f32(const float *x, float *y, int64_t outer, int64_t len, int64_t inner,
+                            int crop, const double *ha, const double *hb, int m,
+                            int accumulate, void *stream);
+int dtcwt_b200_colifilt_f64(const double *x, double *y, int64_t outer, int64_t len, int64_t inner,
+                            int crop, const double *ha, const double *hb, int m,
+                            int accumulate, void *stream);
+
+/* ---- 2-D sub-band packing ---------------------------------------------------
+ * replaces dtcwt/numpy/transform2d.py: q2c (:301-322) and c2q (:324-350).
+ * y is real [n][2h][2w]; z is complex, element (b, band, i, j) at
+ * z + 2*(b*zs_n + band*zs_band + i*zs_row + j*zs_col) (real units), so both the
+ * reference's interleaved (h, w, 6) layout and the planar [6][h][w] layout this
+ * library prefers are expressible.  q2c writes bands band0 and band1; c2q reads
+ * them and scales by gain0 / gain1 (the gain_mask entries, transform2d.py:243).
+ */
+int dtcwt_b200_q2c_f32(const float *y, float *z, int64_t n, int64_t h, int64_t w,
+                       int64_t zs_n, int64_t zs_band, int64_t zs_row, int64_t zs_col,
+                       int band0, int band1, void *stream);
+int dtcwt_b200_q2c_f64(const double *y, double *z, int64_t n, int64_t h, int64_t w,
+                       int64_t zs_n, int64_t zs_band, int64_t zs_row, int64_t zs_col,
+                       int band0, int band1, void *stream);
+int dtcwt_b200_c2q_f32(const float *z, float *y, int64_t n, int64_t h, int64_t w,
+                       int64_t zs_n, int64_t zs_band, int64_t zs_row, int64_t zs_col,
+                       int band0, int band1, double gain0, double gain1, void *stream);
+int dtcwt_b200_c2q_f64(const double *z, double *y, int64_t n, int64_t h, int64_t w,
+                       int64_t zs_n, int64_t zs_band, int64_t zs_row, int64_t zs_col,
+                       int band0, int band1, double gain0, double gain1, void *stream);
+
+/* ---- 1-D sub-band packing ---------------------------------------------------
+ * replaces dtcwt/numpy/transform1d.py:86-88 (Hi[::2] + 1j*Hi[1::2]) and c2q1d
+ * (:186-196).  hi is real [outer][2k][inner]; z is complex [outer][k][inner].
+ * unpack multiplies by `gain` (the 1-D gain_mask entry, transform1d.py:161).
+ */
+int dtcwt_b200_pack1d_f32(const float *hi, float *z, int64_t outer, int64_t k, int64_t inner, void *stream);
+int dtcwt_b200_pack1d_f64(const double *hi, double *z, int64_t outer, int64_t k, int64_t inner, void *stream);
+int dtcwt_b200_unpack1d_f32(const float *z, float *hi, int64_t outer, int64_t k, int64_t inner,
+                            double gain, void *stream);
+int dtcwt_b200_unpack1d_f64(const double *z, double *hi, int64_t outer, int64_t k, int64_t inner,
+                            double gain, void *stream);
+
+/* ---- 3-D sub-band packing ---------------------------------------------------
+ * replaces dtcwt/numpy/transform3d.py: cube2c (:532-579) and c2cube (:581-619).
+ * y is real [n][2a][2b][2c]; z is complex, element (v, chan, i, j, k) at
+ * z + 2*(v*zs_n + chan*zs_chan + i*zs_0 + j*zs_1 + k*zs_2).  The four complex
+ * outputs p,q,r,s go to channels chan0 .. chan0+3.
+ */
+int dtcwt_b200_cube2c_f32(const float *y, float *z, int64_t n, int64_t a, int64_t b, int64_t c,
+                          int64_t zs_n, int64_t zs_chan, int64_t zs_0, int64_t zs_1, int64_t zs_2,
+                          int chan0, void *stream);
+int dtcwt_b200_cube2c_f64(const double *y, double *z, int64_t n, int64_t a, int64_t b, int64_t c,
+                          int64_t zs_n, int64_t zs_chan, int64_t zs_0, int64_t zs_1, int64_t zs_2,
+                          int chan0, void *stream);
+int dtcwt_b200_c2cube_f32(const float *z, float *y, int64_t n, int64_t a, int64_t b, int64_t c,
+                          int64_t zs_n, int64_t zs_chan, int64_t zs_0, int64_t zs_1, int64_t zs_2,
+                          int chan0, void *stream);
+int dtcwt_b200_c2cube_f64(const double *z, double *y, int64_t n, int64_t a, int64_t b, int64_t c,
+                          int64_t zs_n, int64_t zs_chan, int64_t zs_0, int64_t zs_1, int64_t zs_2,
+                          int chan0, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DTCWT_B200_H */
