@@ -104,5 +104,20 @@ def check(code):
         raise RuntimeError("CUDA error %d: %s" % (code, msg))
 
 
+_LAUNCH_HOOK = None
+
+
+def set_launch_hook(hook):
+    """Observer for C-ABI launches: ``hook(symbol, thunk)`` must call ``thunk()`` exactly once.
+    Used by bench.py to count launches and bracket them with CUDA events; None removes it."""
+    global _LAUNCH_HOOK
+    _LAUNCH_HOOK = hook
+
+
 def call(name, dtype_suffix, *args):
-    check(getattr(lib(), "dtcwt_b200_%s_%s" % (name, dtype_suffix))(*args))
+    symbol = "dtcwt_b200_%s_%s" % (name, dtype_suffix)
+    fn = getattr(lib(), symbol)
+    if _LAUNCH_HOOK is None:
+        check(fn(*args))
+    else:
+        _LAUNCH_HOOK(symbol, lambda: check(fn(*args)))
