@@ -33,7 +33,12 @@ _TYPED = {
     "cube2c": [_P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _P],
     "c2cube": [_P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _P],
 }
-_F32_ONLY = {}
+_F32_ONLY = {
+    "fwd2d_level1": [_P, _P, _P, _L, _L, _L, _I, _I, _TAPS, _I, _TAPS, _I, _L, _L, _L, _P],
+    "fwd2d_levelq": [_P, _P, _P, _L, _L, _L, _I, _I, _TAPS, _TAPS, _TAPS, _TAPS, _I, _L, _L, _L, _P],
+    "inv2d_levelq": [_P, _P, _P, _L, _L, _L, _I, _I, _TAPS, _TAPS, _TAPS, _TAPS, _I, _TAPS, _L, _L, _L, _P],
+    "inv2d_level1": [_P, _P, _P, _L, _L, _L, _TAPS, _I, _TAPS, _I, _TAPS, _L, _L, _L, _P],
+}
 
 EXPORTS = (["dtcwt_b200_version", "dtcwt_b200_error_string", "dtcwt_b200_is_device_build"]
            + ["dtcwt_b200_%s_%s" % (n, s) for n in _TYPED for s in ("f32", "f64")]
@@ -112,6 +117,29 @@ def set_launch_hook(hook):
     Used by bench.py to count launches and bracket them with CUDA events; None removes it."""
     global _LAUNCH_HOOK
     _LAUNCH_HOOK = hook
+
+
+E_UNSUPPORTED = -2
+
+
+def call_optional(name, dtype_suffix, *args):
+    """Like :func:`call`, but a DTCWT_B200_EUNSUPPORTED answer returns False (nothing was launched)
+    so the caller can compose the same result from the generic CUDA kernels."""
+    symbol = "dtcwt_b200_%s_%s" % (name, dtype_suffix)
+    fn = getattr(lib(), symbol)
+    out = []
+
+    def thunk():
+        code = fn(*args)
+        if code != E_UNSUPPORTED:
+            check(code)
+        out.append(code)
+
+    if _LAUNCH_HOOK is None:
+        thunk()
+    else:
+        _LAUNCH_HOOK(symbol, thunk)
+    return out[0] == 0
 
 
 def call(name, dtype_suffix, *args):

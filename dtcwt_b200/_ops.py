@@ -184,6 +184,85 @@ def c2q(z, band0, band1, gain0, gain1):
     return y
 
 
+# ----------------------------------------------------------------------------- fused 2-D levels
+FUSED_ENABLED = True      # tests flip this to compare the fused kernels with the generic composition
+
+
+def _fused_ok(*tensors):
+    return FUSED_ENABLED and all(t.dtype in (torch.float32, torch.complex64) for t in tensors)
+
+
+def fwd2d_level1(x, h0o, h1o, pad_hi):
+    """Fused level 1 of the 2-D forward transform: x [n][H][W] -> (LoLo [n][H'][W'], Yh planar [n][6][H'/2][W'/2])
+    or None when the fused kernels do not cover the request."""
+    if not _fused_ok(x):
+        return None
+    n, r, c = x.shape
+    Lr, Lc = r + pad_hi[0], c + pad_hi[1]
+    k0, p0, m0 = _taps(h0o)
+    k1, p1, m1 = _taps(h1o)
+    lolo = torch.empty((n, Lr, Lc), dtype=x.dtype, device=x.device)
+    yh = new_highpass(n, 6, (Lr // 2, Lc // 2), x.dtype, x.device)
+    with _on_device(x):
+        ok = _lib.call_optional("fwd2d_level1", "f32", _ptr(x), _ptr(lolo), _ptr(yh), n, r, c, pad_hi[0], pad_hi[1],
+                                p0, m0, p1, m1, yh.stride(0), yh.stride(1), yh.stride(2), _stream(x))
+    return (lolo, yh) if ok else None
+
+
+def fwd2d_levelq(x, lo_a, lo_b, hi_a, hi_b, pad):
+    """Fused level >= 2 of the 2-D forward transform; pad = (pad_r, pad_c) in {0, 1} (one sample each side)."""
+    if not _fused_ok(x):
+        return None
+    n, r, c = x.shape
+    Lr, Lc = r + 2 * pad[0], c + 2 * pad[1]
+    taps = [_taps(h) for h in (lo_a, lo_b, hi_a, hi_b)]
+    if len({t[2] for t in taps}) != 1:
+        return None
+    lolo = torch.empty((n, Lr // 2, Lc // 2), dtype=x.dtype, device=x.device)
+    yh = new_highpass(n, 6, (Lr // 4, Lc // 4), x.dtype, x.device)
+    with _on_device(x):
+        ok = _lib.call_optional("fwd2d_levelq", "f32", _ptr(x), _ptr(lolo), _ptr(yh), n, r, c, pad[0], pad[1],
+                                taps[0][1], taps[1][1], taps[2][1], taps[3][1], taps[0][2],
+                                yh.stride(0), yh.stride(1), yh.stride(2), _stream(x))
+    return (lolo, yh) if ok else None
+
+
+def _gain6(gain):
+    g = np.ascontiguousarray(np.asarray(gain, dtype=np.float64).reshape(6))
+    return g, g.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def inv2d_levelq(z, yh, lo_a, lo_b, hi_a, hi_b, gain, crop):
+    """Fused level >= 2 of the 2-D inverse: z [n][r][c], yh planar [n][6][r/2][c/2] -> [n][2r-2crop_r][2c-2crop_c]."""
+    if not _fused_ok(z, yh) or not yh.is_contiguous():
+        return None
+    n, r, c = z.shape
+    taps = [_taps(h) for h in (lo_a, lo_b, hi_a, hi_b)]
+    if len({t[2] for t in taps}) != 1:
+        return None
+    gk, gp = _gain6(gain)
+    out = torch.empty((n, 2 * r - 2 * crop[0], 2 * c - 2 * crop[1]), dtype=z.dtype, device=z.device)
+    with _on_device(z):
+        ok = _lib.call_optional("inv2d_levelq", "f32", _ptr(z), _ptr(yh), _ptr(out), n, r, c, crop[0], crop[1],
+                                taps[0][1], taps[1][1], taps[2][1], taps[3][1], taps[0][2], gp,
+                                yh.stride(0), yh.stride(1), yh.stride(2), _stream(z))
+    return out if ok else None
+
+
+def inv2d_level1(z, yh, g0o, g1o, gain):
+    if not _fused_ok(z, yh) or not yh.is_contiguous():
+        return None
+    n, r, c = z.shape
+    k0, p0, m0 = _taps(g0o)
+    k1, p1, m1 = _taps(g1o)
+    gk, gp = _gain6(gain)
+    out = torch.empty((n, r, c), dtype=z.dtype, device=z.device)
+    with _on_device(z):
+        ok = _lib.call_optional("inv2d_level1", "f32", _ptr(z), _ptr(yh), _ptr(out), n, r, c, p0, m0, p1, m1, gp,
+                                yh.stride(0), yh.stride(1), yh.stride(2), _stream(z))
+    return out if ok else None
+
+
 # ----------------------------------------------------------------------------- 1-D packing
 def pack1d(hi):
     """real [2k][c] -> complex [k][c]: even rows real part, odd rows imaginary part."""

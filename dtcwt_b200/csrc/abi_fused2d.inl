@@ -1,0 +1,188 @@
+// C-ABI entry points of the fused per-level 2-D kernels (fused2d.cuh).  Included by
+// dtcwt_b200.cu (device build) and tests/emu/emu.cpp (host emulator); the including
+// file provides
+//   template <class K> int launch_fwd2d(typename K::Args&, void* stream);
+//   template <class K> int launch_inv2d(typename K::Args&, void* stream);
+// Requests outside what the fused kernels cover return DTCWT_B200_EUNSUPPORTED; the
+// host layer then composes the level from the generic CUDA kernels instead.
+
+namespace dtcwt {
+
+static const double kInvSqrt2 = 0.70710678118654752440;
+static const int kFusedMinSide = 32;      // smaller images: reflection may wrap twice -> generic kernels
+
+static void clear_taps(PhaseTaps& t) {
+    for (int p = 0; p < kMaxPhases; ++p)
+        for (int k = 0; k < kMaxPhaseTaps; ++k) t.t[p][k] = 0.f;
+}
+
+// colfilter (lowlevel.py:69-78): Y[i] = sum_k h[k] X[i + c - k], c = (m-1)/2; with k' = K-1-k (K >= m, centred)
+// out[i] = sum_k' t[k'] in[i - (K-1)/2 + k'].
+static void taps_col(PhaseTaps& t, const double* h, int m, int K, double scale) {
+    clear_taps(t);
+    const int z = (K - m) / 2;
+    for (int k = 0; k < m; ++k) t.t[0][z + (m - 1 - k)] = (float)((double)(float)h[k] * scale);
+}
+
+// coldfilt (lowlevel.py:131-152): Ya[i] = sum_j ha[j] X[4i + m - 2j], Yb[i] = sum_j hb[j] X[4i + m + 1 - 2j];
+// phase 0 of the output pair is Ya when pos else Yb.  Reversed: t[j'] = f[m-1-j'], in[4i - m + 2 + delta + 2j'].
+static void taps_dec(PhaseTaps& t, const double* ha, const double* hb, int m, bool pos, double scale) {
+    clear_taps(t);
+    for (int ph = 0; ph < 2; ++ph) {
+        const double* f = ((ph == 0) == pos) ? ha : hb;
+        for (int j = 0; j < m; ++j) t.t[ph][j] = (float)((double)(float)f[m - 1 - j] * scale);
+    }
+}
+
+// colifilt (lowlevel.py:205-258): Y[4i+ph] = sum_k f_ph[2k + tp_ph] X[2i + m2 - 2k + off_ph], f_ph = hb for odd ph.
+// Reversed: t[ph][k'] = f_ph[2(m2-1-k') + tp_ph], in[2i - m2 + 2 + off_ph + 2k'].
+static void taps_int(PhaseTaps& t, const double* ha, const double* hb, int m, bool pos) {
+    clear_taps(t);
+    int tp[4], off[4];
+    colifilt_phase_tables(m, pos, tp, off);
+    const int m2 = m / 2;
+    for (int ph = 0; ph < 4; ++ph) {
+        const double* f = (ph & 1) ? hb : ha;
+        for (int k = 0; k < m2; ++k) t.t[ph][k] = (float)f[2 * (m2 - 1 - k) + tp[ph]];
+    }
+}
+
+static bool aligned_to(const void* p, size_t a) { return ((uintptr_t)p % a) == 0; }
+
+// ------------------------------------------------------------------ kernel instances
+// level 1: (lowpass taps, highpass taps) of the shipped biorthogonal families, longest first
+typedef Fwd2d<SpecCol<13>, SpecCol<19>, 64, 64, 8> FwdL1_13_19;     // near_sym_b (+ anything shorter, zero-padded)
+typedef Fwd2d<SpecCol<5>, SpecCol<7>, 64, 64, 8> FwdL1_5_7;         // near_sym_a (+ legall 5/3)
+typedef Fwd2d<SpecCol<19>, SpecCol<19>, 64, 64, 8> FwdL1_19_19;     // any odd pair up to 19 taps
+typedef Inv2d<SpecCol<19>, SpecCol<13>, 64, 64, 8> InvL1_19_13;
+typedef Inv2d<SpecCol<7>, SpecCol<5>, 64, 64, 8> InvL1_7_5;
+typedef Inv2d<SpecCol<19>, SpecCol<19>, 64, 64, 8> InvL1_19_19;
+// levels >= 2: q-shift pairs; every shipped family has a positive lowpass and a negative highpass tap correlation
+template <int M> struct FwdLq { typedef Fwd2d<SpecDec<M, true>, SpecDec<M, false>, 32, 16, 2> type; };
+template <int M> struct InvLq { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 16, 16, 2> type; };
+
+static int fwd_common(Fwd2dArgs& a, const float* x, float* lolo, float* yh, int64_t n, int64_t rows, int64_t cols,
+                      int pr_lo, int pr_hi, int pc_lo, int pc_hi, int P, int Q, int64_t zs_n, int64_t zs_band,
+                      int64_t zs_row) {
+    if (!x || !lolo || !yh || n < 0 || rows < 1 || cols < 1) return DTCWT_B200_EINVAL;
+    if (n > 65535 || rows < kFusedMinSide || cols < kFusedMinSide || rows > (1 << 24) || cols > (1 << 24))
+        return DTCWT_B200_EUNSUPPORTED;
+    if (!aligned_to(lolo, 8) || !aligned_to(yh, 8) || !aligned_to(x, 4)) return DTCWT_B200_EUNSUPPORTED;
+    a.x = x; a.lolo = lolo; a.yh = yh;
+    a.n = (int)n; a.rows = (int)rows; a.cols = (int)cols;
+    a.pr_lo = pr_lo; a.pc_lo = pc_lo;
+    a.Lr = (int)rows + pr_lo + pr_hi; a.Lc = (int)cols + pc_lo + pc_hi;
+    if ((a.Lr % (2 * Q / P)) || (a.Lc % (2 * Q / P))) return DTCWT_B200_EINVAL;   // level 1: even; level q: multiple of 4
+    a.out_rows = P * a.Lr / Q; a.out_cols = P * a.Lc / Q;
+    a.zs_n = zs_n; a.zs_band = zs_band; a.zs_row = zs_row;
+    a.use_tma = 0;
+    return DTCWT_B200_OK;
+}
+
+static int inv_common(Inv2dArgs& a, const float* z, const float* yh, float* out, int64_t n, int64_t rows,
+                      int64_t cols, int crop_r, int crop_c, int P, int Q, const double* gain, int64_t zs_n,
+                      int64_t zs_band, int64_t zs_row) {
+    if (!z || !yh || !out || !gain || n < 0 || rows < 2 || cols < 2 || (rows & 1) || (cols & 1)) return DTCWT_B200_EINVAL;
+    if (crop_r < 0 || crop_r > 1 || crop_c < 0 || crop_c > 1) return DTCWT_B200_EINVAL;
+    if (n > 65535 || rows < kFusedMinSide || cols < kFusedMinSide || rows > (1 << 24) || cols > (1 << 24))
+        return DTCWT_B200_EUNSUPPORTED;
+    if (!aligned_to(z, 8) || !aligned_to(yh, 8) || !aligned_to(out, 8)) return DTCWT_B200_EUNSUPPORTED;
+    a.z = z; a.yh = yh; a.out = out;
+    a.n = (int)n; a.rows = (int)rows; a.cols = (int)cols;
+    a.crop_r = crop_r; a.crop_c = crop_c;
+    a.out_rows = P * (int)rows / Q - 2 * crop_r; a.out_cols = P * (int)cols / Q - 2 * crop_c;
+    a.zs_n = zs_n; a.zs_band = zs_band; a.zs_row = zs_row;
+    for (int b = 0; b < 6; ++b) a.gain[b] = (float)(gain[b] * kInvSqrt2);
+    return DTCWT_B200_OK;
+}
+
+}  // namespace dtcwt
+
+using namespace dtcwt;
+
+extern "C" {
+
+// transform2d.py:112-130 (level 1 of Transform2d.forward), 4-tuple biort
+int dtcwt_b200_fwd2d_level1_f32(const float* x, float* lolo, float* yh, int64_t n, int64_t rows, int64_t cols,
+                                int pad_r_hi, int pad_c_hi, const double* h0o, int m0, const double* h1o, int m1,
+                                int64_t zs_n, int64_t zs_band, int64_t zs_row, void* stream) {
+    if (!h0o || !h1o || m0 < 1 || m1 < 1 || pad_r_hi < 0 || pad_r_hi > 1 || pad_c_hi < 0 || pad_c_hi > 1)
+        return DTCWT_B200_EINVAL;
+    if (!(m0 & 1) || !(m1 & 1) || m0 > 19 || m1 > 19) return DTCWT_B200_EUNSUPPORTED;
+    Fwd2dArgs a;
+    const int rc = fwd_common(a, x, lolo, yh, n, rows, cols, 0, pad_r_hi, 0, pad_c_hi, 1, 1, zs_n, zs_band, zs_row);
+    if (rc) return rc;
+    const int K0 = (m0 <= 5 && m1 <= 7) ? 5 : (m0 <= 13 ? 13 : 19);
+    const int K1 = (K0 == 5) ? 7 : 19;
+    taps_col(a.h0, h0o, m0, K0, 1.0);
+    taps_col(a.h1s, h1o, m1, K1, kInvSqrt2);
+    taps_col(a.v0, h0o, m0, K0, 1.0);
+    taps_col(a.v1, h1o, m1, K1, 1.0);
+    taps_col(a.v1s, h1o, m1, K1, kInvSqrt2);
+    if (K0 == 5) return launch_fwd2d<FwdL1_5_7>(a, stream);
+    if (K0 == 13) return launch_fwd2d<FwdL1_13_19>(a, stream);
+    return launch_fwd2d<FwdL1_19_19>(a, stream);
+}
+
+// transform2d.py:132-160 (levels >= 2 of Transform2d.forward), 8-tuple qshift.  (lo_a, lo_b) and (hi_a, hi_b) are
+// coldfilt's (ha, hb) arguments, i.e. the reference passes (h0b, h0a) and (h1b, h1a).  pad_r / pad_c = 1 extends
+// the input by one replicated sample on each side of that axis (transform2d.py:134-140).
+int dtcwt_b200_fwd2d_levelq_f32(const float* x, float* lolo, float* yh, int64_t n, int64_t rows, int64_t cols,
+                                int pad_r, int pad_c, const double* lo_a, const double* lo_b, const double* hi_a,
+                                const double* hi_b, int m, int64_t zs_n, int64_t zs_band, int64_t zs_row,
+                                void* stream) {
+    if (!lo_a || !lo_b || !hi_a || !hi_b || m < 2 || (m & 1) || pad_r < 0 || pad_r > 1 || pad_c < 0 || pad_c > 1)
+        return DTCWT_B200_EINVAL;
+    if (m != 10 && m != 14 && m != 18) return DTCWT_B200_EUNSUPPORTED;
+    if (!(tap_dot(lo_a, lo_b, m) > 0) || (tap_dot(hi_a, hi_b, m) > 0)) return DTCWT_B200_EUNSUPPORTED;
+    Fwd2dArgs a;
+    const int rc = fwd_common(a, x, lolo, yh, n, rows, cols, pad_r, pad_r, pad_c, pad_c, 2, 4, zs_n, zs_band, zs_row);
+    if (rc) return rc;
+    taps_dec(a.h0, lo_a, lo_b, m, true, 1.0);
+    taps_dec(a.h1s, hi_a, hi_b, m, false, kInvSqrt2);
+    taps_dec(a.v0, lo_a, lo_b, m, true, 1.0);
+    taps_dec(a.v1, hi_a, hi_b, m, false, 1.0);
+    taps_dec(a.v1s, hi_a, hi_b, m, false, kInvSqrt2);
+    if (m == 10) return launch_fwd2d<FwdLq<10>::type>(a, stream);
+    if (m == 14) return launch_fwd2d<FwdLq<14>::type>(a, stream);
+    return launch_fwd2d<FwdLq<18>::type>(a, stream);
+}
+
+// transform2d.py:240-273 (levels >= 2 of Transform2d.inverse).  (lo_a, lo_b), (hi_a, hi_b) are colifilt's (ha, hb):
+// the reference passes (g0b, g0a) and (g1b, g1a).  gain[6] is this level's gain_mask column.
+int dtcwt_b200_inv2d_levelq_f32(const float* z, const float* yh, float* out, int64_t n, int64_t rows, int64_t cols,
+                                int crop_r, int crop_c, const double* lo_a, const double* lo_b, const double* hi_a,
+                                const double* hi_b, int m, const double* gain, int64_t zs_n, int64_t zs_band,
+                                int64_t zs_row, void* stream) {
+    if (!lo_a || !lo_b || !hi_a || !hi_b || m < 2 || (m & 1)) return DTCWT_B200_EINVAL;
+    if (m != 10 && m != 14 && m != 18) return DTCWT_B200_EUNSUPPORTED;
+    if (!(tap_dot(lo_a, lo_b, m) > 0) || (tap_dot(hi_a, hi_b, m) > 0)) return DTCWT_B200_EUNSUPPORTED;
+    Inv2dArgs a;
+    const int rc = inv_common(a, z, yh, out, n, rows, cols, crop_r, crop_c, 4, 2, gain, zs_n, zs_band, zs_row);
+    if (rc) return rc;
+    taps_int(a.g0, lo_a, lo_b, m, true);
+    taps_int(a.g1, hi_a, hi_b, m, false);
+    if (m == 10) return launch_inv2d<InvLq<10>::type>(a, stream);
+    if (m == 14) return launch_inv2d<InvLq<14>::type>(a, stream);
+    return launch_inv2d<InvLq<18>::type>(a, stream);
+}
+
+// transform2d.py:275-293 (level 1 of Transform2d.inverse), 4-tuple biort
+int dtcwt_b200_inv2d_level1_f32(const float* z, const float* yh, float* out, int64_t n, int64_t rows, int64_t cols,
+                                const double* g0o, int m0, const double* g1o, int m1, const double* gain,
+                                int64_t zs_n, int64_t zs_band, int64_t zs_row, void* stream) {
+    if (!g0o || !g1o || m0 < 1 || m1 < 1) return DTCWT_B200_EINVAL;
+    if (!(m0 & 1) || !(m1 & 1) || m0 > 19 || m1 > 19) return DTCWT_B200_EUNSUPPORTED;
+    Inv2dArgs a;
+    const int rc = inv_common(a, z, yh, out, n, rows, cols, 0, 0, 1, 1, gain, zs_n, zs_band, zs_row);
+    if (rc) return rc;
+    const int K1 = (m0 <= 7 && m1 <= 5) ? 5 : (m1 <= 13 ? 13 : 19);
+    const int K0 = (K1 == 5) ? 7 : 19;
+    taps_col(a.g0, g0o, m0, K0, 1.0);
+    taps_col(a.g1, g1o, m1, K1, 1.0);
+    if (K1 == 5) return launch_inv2d<InvL1_7_5>(a, stream);
+    if (K1 == 13) return launch_inv2d<InvL1_19_13>(a, stream);
+    return launch_inv2d<InvL1_19_19>(a, stream);
+}
+
+}  // extern "C"

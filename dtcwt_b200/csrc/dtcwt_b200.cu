@@ -3,6 +3,7 @@
 #include <stdio.h>
 
 #include "generic_kernels.cuh"
+#include "fused2d.cuh"
 
 namespace dtcwt {
 
@@ -28,6 +29,8 @@ static int launch_1d(const typename Elem::Args& a, void* stream) {
 }  // namespace dtcwt
 
 #include "abi_generic.inl"
+#include "fused2d_launch.cuh"
+#include "abi_fused2d.inl"
 
 extern "C" {
 

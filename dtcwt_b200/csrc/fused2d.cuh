@@ -1,0 +1,501 @@
+// Fused per-level 2-D DT-CWT kernels (float32).
+//
+// One CTA transforms one tile of one image through a whole level:
+//
+//   forward  (reference transform2d.py:112-160)   X tile --TMA--> smem
+//            row pass   A = H:h0(X), B = H:h1(X)/sqrt2            (smem -> registers -> smem)
+//            column pass LoLo = V:h0(A), q2c(V:h1(A)/sqrt2), q2c(V:h0(B)), q2c(V:h1(B))
+//            -> LoLo tile and the six complex sub-bands go straight from registers to HBM
+//   inverse  (reference transform2d.py:240-293)   c2q is applied while the tile is loaded,
+//            row pass   p1 = H:g0(Z) + H:g1(hl),  p2 = H:g0(lh) + H:g1(hh)
+//            column pass out = V:g0(p1) + V:g1(p2)
+//
+// (The reference filters columns first; the passes commute, only rounding differs.)
+// Every input sample is read from HBM once per level (plus the tile halo, which
+// neighbouring CTAs find in L2) and every output is written once.
+//
+// All three reference filters are instances of one polyphase form
+//     out[P*i + ph] = sum_{k<K} t[ph][k] * in[Q*i + b(ph) + S*k]
+//   colfilter (lowlevel.py:47-80)    P=1 Q=1 S=1 K=m      b = -(m-1)/2
+//   coldfilt  (lowlevel.py:82-154)   P=2 Q=4 S=2 K=m      b = -m+2+delta(ph)
+//   colifilt  (lowlevel.py:156-260)  P=4 Q=2 S=2 K=m/2    b = -m/2+2+off(ph)
+// with the structure (P,Q,S,K,b) fixed at compile time and the taps t[ph][k]
+// prepared on the host (abi_fused2d.inl) and passed by value: they live in the
+// constant bank and feed FFMA directly.
+//
+// The bodies are split into phases separated by block barriers; tests/emu runs
+// the same phases thread by thread on the host (DTCWT_EMU).
+#pragma once
+#include "common.cuh"
+
+namespace dtcwt {
+
+#ifdef DTCWT_EMU
+struct alignas(8) F2 { float x, y; };
+struct alignas(16) F4 { float x, y, z, w; };
+#else
+typedef float2 F2;
+typedef float4 F4;
+#endif
+
+constexpr int kFusedThreads = 256;
+constexpr int kMaxPhases = 4;
+constexpr int kMaxPhaseTaps = 19;
+
+struct PhaseTaps {
+    float t[kMaxPhases][kMaxPhaseTaps];
+};
+
+DTCWT_HD constexpr int cmax(int a, int b) { return a > b ? a : b; }
+DTCWT_HD constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ------------------------------------------------------------------ filter structure
+template <int K_>
+struct SpecCol {                       // colfilter, K odd (shorter filters are zero-padded, centred)
+    static constexpr int P = 1, Q = 1, S = 1, K = K_;
+    static DTCWT_HD constexpr int b(int) { return -(K_ - 1) / 2; }
+};
+
+template <int M, bool POS>
+struct SpecDec {                       // coldfilt: phase 0 is Ya (delta 0) when POS else Yb (delta 1)
+    static constexpr int P = 2, Q = 4, S = 2, K = M;
+    static DTCWT_HD constexpr int b(int ph) { return -M + 2 + (((ph == 0) == POS) ? 0 : 1); }
+};
+
+template <int M, bool POS>
+struct SpecInt {                       // colifilt (phase tables: abi_generic.inl colifilt_phase_tables)
+    static constexpr int P = 4, Q = 2, S = 2, K = M / 2;
+    static DTCWT_HD constexpr int off(int ph) {
+        return ((M / 2) & 1) ? (POS ? ((ph & 1) ? 0 : -1) : ((ph & 1) ? -1 : 0))
+                             : (POS ? ph - 2 : (ph == 0 ? -1 : ph == 1 ? -2 : ph == 2 ? 1 : 0));
+    }
+    static DTCWT_HD constexpr int b(int ph) { return -(M / 2) + 2 + off(ph); }
+};
+
+template <class F>
+DTCWT_HD constexpr int spec_lo() {     // input samples needed before the first sample of a group
+    int m = 0;
+    for (int ph = 0; ph < F::P; ++ph) m = cmax(m, -F::b(ph));
+    return m;
+}
+template <class F>
+DTCWT_HD constexpr int spec_hi() {     // ... and after its last sample
+    int m = 0;
+    for (int ph = 0; ph < F::P; ++ph) m = cmax(m, F::b(ph) + F::S * (F::K - 1) - (F::Q - 1));
+    return m;
+}
+
+// acc[P*ii+ph] += sum_k t[ph][k] * w[Q*ii + b(ph) + S*k + HALO]   (register window, all indices static)
+template <class F, int NG, int HALO, int WN>
+DTCWT_D void fir_gather(const float (&w)[WN], const PhaseTaps& t, float (&acc)[F::P * NG]) {
+#pragma unroll
+    for (int ii = 0; ii < NG; ++ii) {
+#pragma unroll
+        for (int ph = 0; ph < F::P; ++ph) {
+            float s = acc[F::P * ii + ph];
+#pragma unroll
+            for (int k = 0; k < F::K; ++k) s = fmaf(t.t[ph][k], w[F::Q * ii + F::b(ph) + F::S * k + HALO], s);
+            acc[F::P * ii + ph] = s;
+        }
+    }
+}
+
+// Input row j (relative to the window start, HALO rows before the first group) contributes to
+// the outputs whose support contains it; j is a compile-time constant after unrolling.
+template <class F, int NG, int HALO>
+DTCWT_D void fir_scatter(const int j, const F2 v, const PhaseTaps& t, F2 (&acc)[F::P * NG]) {
+#pragma unroll
+    for (int ii = 0; ii < NG; ++ii) {
+#pragma unroll
+        for (int ph = 0; ph < F::P; ++ph) {
+            const int num = j - HALO - F::Q * ii - F::b(ph);
+            if (num >= 0 && (num % F::S) == 0 && (num / F::S) < F::K) {
+                const float c = t.t[ph][num / F::S];
+                acc[F::P * ii + ph].x = fmaf(c, v.x, acc[F::P * ii + ph].x);
+                acc[F::P * ii + ph].y = fmaf(c, v.y, acc[F::P * ii + ph].y);
+            }
+        }
+    }
+}
+template <class F, int NG, int HALO>
+DTCWT_HD constexpr bool fir_row_used(const int j) {
+    for (int ii = 0; ii < NG; ++ii)
+        for (int ph = 0; ph < F::P; ++ph) {
+            const int num = j - HALO - F::Q * ii - F::b(ph);
+            if (num >= 0 && (num % F::S) == 0 && (num / F::S) < F::K) return true;
+        }
+    return false;
+}
+
+// =============================================================================== forward level
+struct Fwd2dArgs {
+    const float* x;                 // [n][rows][cols]
+    float* lolo;                    // [n][out_rows][out_cols]
+    float* yh;                      // complex, planar: (b, band, i, j) at 2*(b*zs_n + band*zs_band + i*zs_row + j)
+    int n, rows, cols;              // stored input size
+    int pr_lo, pc_lo;               // replicate padding on the low side (high side implied by Lr/Lc)
+    int Lr, Lc;                     // logical (padded) size
+    int out_rows, out_cols;         // P*Lr/Q, P*Lc/Q
+    int use_tma;
+    int64_t zs_n, zs_band, zs_row;
+    PhaseTaps h0, h1s;              // row pass: lowpass, highpass/sqrt2
+    PhaseTaps v0, v1, v1s;          // column pass: lowpass, highpass, highpass/sqrt2
+};
+
+template <class H0, class H1, int GH_, int GW_, int NGV_>
+struct Fwd2d {
+    typedef Fwd2dArgs Args;
+    static constexpr int P = H0::P, Q = H0::Q;
+    static constexpr int GH = GH_, GW = GW_, NGV = NGV_;
+    static constexpr int NGH = 4 / Q;                       // a row task covers 4 input columns
+    static constexpr int HL = cmax(spec_lo<H0>(), spec_lo<H1>());
+    static constexpr int HR = cmax(spec_hi<H0>(), spec_hi<H1>());
+    static constexpr int HLA = round_up(HL, 4), HRA = round_up(HR, 4);
+    static constexpr int RX = Q * GH + HL + HR;             // input tile rows
+    static constexpr int CX = Q * GW + HLA + HRA;           // input tile columns (multiple of 4)
+    static constexpr int CA = P * GW;                       // columns of the row-pass outputs
+    static constexpr int WN = 4 + HLA + HRA;                // register window of a row task
+    static constexpr int NSEG = GW / NGH;
+    static constexpr int NR = Q * NGV + HL + HR;            // input rows of a column task
+    static constexpr int NOUT = P * NGV;                    // output rows of a column task (even)
+    static constexpr int kSmemFloats = RX * CX + 2 * RX * CA;
+    static constexpr int kThreads = kFusedThreads;
+    static constexpr int kPhases = 5;
+    static_assert(P == H1::P && Q == H1::Q, "filter pair must share its rate");
+    static_assert((NOUT % 2) == 0 && (GH % NGV) == 0 && (GW % NGH) == 0 && (CA % 2) == 0, "tile shape");
+    static_assert(P * NGH == 4 || P * NGH == 2, "row task writes a float4 or float2");
+
+    static DTCWT_HD int tiles_r(const Args& a) { return (a.Lr + Q * GH - 1) / (Q * GH); }
+    static DTCWT_HD int tiles_c(const Args& a) { return (a.Lc + Q * GW - 1) / (Q * GW); }
+    // logical coordinates of smem element (0, 0)
+    static DTCWT_HD int row0(int by) { return Q * GH * by - HL; }
+    static DTCWT_HD int col0(int bx) { return Q * GW * bx - HLA; }
+
+    // phase 0: plain loads of the tile, zero outside the stored array (what TMA produces; used when
+    // the row pitch is not a multiple of 16 bytes, and by the host emulator)
+    static DTCWT_D void phase_load(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        if (a.use_tma) return;
+        const float* img = a.x + (int64_t)bz * a.rows * a.cols;
+        const int r0 = row0(by) - a.pr_lo, c0 = col0(bx) - a.pc_lo;
+        for (int e = tid; e < RX * CX; e += kThreads) {
+            const int lr = e / CX, lc = e - lr * CX;
+            const int r = r0 + lr, c = c0 + lc;
+            sm[e] = (r >= 0 && r < a.rows && c >= 0 && c < a.cols) ? img[(int64_t)r * a.cols + c] : 0.f;
+        }
+    }
+
+    // smem index that holds the sample logical index L (outside the stored range) mirrors, or -1
+    static DTCWT_HD int mirror_src(int L, int Ltot, int pad_lo, int len, int L0, int extent) {
+        const int s = L - pad_lo;
+        if (s >= 0 && s < len) return -2;                                  // directly loaded
+        const int l = unpad(reflect_any(L, Ltot), pad_lo, len) + pad_lo - L0;
+        return (l >= 0 && l < extent) ? l : -1;
+    }
+    static DTCWT_HD bool touches_edge(int L0, int extent, int pad_lo, int len) {
+        return (L0 - pad_lo < 0) || (L0 + extent - pad_lo > len);
+    }
+
+    // phase 1 / 2: symmetric extension (utils.py:136-153) of tiles on the image border, inside smem
+    static DTCWT_D void phase_patch_rows(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        const int L0 = row0(by);
+        if (!touches_edge(L0, RX, a.pr_lo, a.rows)) return;
+        for (int e = tid; e < RX * CX; e += kThreads) {
+            const int lr = e / CX, lc = e - lr * CX;
+            const int src = mirror_src(L0 + lr, a.Lr, a.pr_lo, a.rows, L0, RX);
+            if (src >= 0) sm[e] = sm[src * CX + lc];
+        }
+    }
+    static DTCWT_D void phase_patch_cols(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        const int L0 = col0(bx);
+        if (!touches_edge(L0, CX, a.pc_lo, a.cols)) return;
+        for (int e = tid; e < RX * CX; e += kThreads) {
+            const int lr = e / CX, lc = e - lr * CX;
+            const int src = mirror_src(L0 + lc, a.Lc, a.pc_lo, a.cols, L0, CX);
+            if (src >= 0) sm[e] = sm[lr * CX + src];
+        }
+    }
+
+    // phase 3: row pass, one task = one tile row x 4 input columns
+    static DTCWT_D void phase_rows(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        const float* Xs = sm;
+        float* As = sm + RX * CX;
+        float* Bs = As + RX * CA;
+        for (int task = tid; task < RX * NSEG; task += kThreads) {
+            const int lr = task / NSEG, seg = task - lr * NSEG;
+            float w[WN];
+            const F4* src = reinterpret_cast<const F4*>(Xs + lr * CX + seg * 4);
+#pragma unroll
+            for (int c = 0; c < WN / 4; ++c) {
+                const F4 v = src[c];
+                w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+            }
+            float oa[P * NGH], ob[P * NGH];
+#pragma unroll
+            for (int i = 0; i < P * NGH; ++i) { oa[i] = 0.f; ob[i] = 0.f; }
+            fir_gather<H0, NGH, HLA, WN>(w, a.h0, oa);
+            fir_gather<H1, NGH, HLA, WN>(w, a.h1s, ob);
+            float* da = As + lr * CA + seg * (P * NGH);
+            float* db = Bs + lr * CA + seg * (P * NGH);
+            if (P * NGH == 4) {
+                F4 va, vb;
+                va.x = oa[0]; va.y = oa[1]; va.z = oa[2 % (P * NGH)]; va.w = oa[3 % (P * NGH)];
+                vb.x = ob[0]; vb.y = ob[1]; vb.z = ob[2 % (P * NGH)]; vb.w = ob[3 % (P * NGH)];
+                *reinterpret_cast<F4*>(da) = va;
+                *reinterpret_cast<F4*>(db) = vb;
+            } else {
+                F2 va, vb;
+                va.x = oa[0]; va.y = oa[1];
+                vb.x = ob[0]; vb.y = ob[1];
+                *reinterpret_cast<F2*>(da) = va;
+                *reinterpret_cast<F2*>(db) = vb;
+            }
+        }
+    }
+
+    // q2c of NOUT rows x 2 columns (transform2d.py:301-322; the 1/sqrt2 is already in the taps)
+    static DTCWT_D void store_q2c(const Args& a, const F2 (&y)[NOUT], int bz, int gi0, int gj, int band0, int band1) {
+        if (gj >= a.out_cols / 2) return;
+        float* z = a.yh + 2 * ((int64_t)bz * a.zs_n + gj);
+#pragma unroll
+        for (int q = 0; q < NOUT / 2; ++q) {
+            const int gi = gi0 + q;
+            if (gi < a.out_rows / 2) {
+                const float A = y[2 * q].x, B = y[2 * q].y, C = y[2 * q + 1].x, D = y[2 * q + 1].y;
+                F2 z0, z1;
+                z0.x = A - D; z0.y = B + C;
+                z1.x = A + D; z1.y = B - C;
+                *reinterpret_cast<F2*>(z + 2 * (band0 * a.zs_band + gi * a.zs_row)) = z0;
+                *reinterpret_cast<F2*>(z + 2 * (band1 * a.zs_band + gi * a.zs_row)) = z1;
+            }
+        }
+    }
+
+    // phase 4: column pass, one task = 2 adjacent columns x NGV groups of rows; results leave from registers
+    static DTCWT_D void phase_cols(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        const float* As = sm + RX * CX;
+        const float* Bs = As + RX * CA;
+        for (int task = tid; task < (CA / 2) * (GH / NGV); task += kThreads) {
+            const int strip = task / (CA / 2), cp = task - strip * (CA / 2);
+            const int lrow = Q * NGV * strip;
+            const int orow = P * (GH * by + NGV * strip);        // first output row (LoLo coordinates)
+            const int ocol = P * GW * bx + 2 * cp;
+            F2 lo[NOUT], hi[NOUT];
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i) { lo[i].x = lo[i].y = 0.f; hi[i].x = hi[i].y = 0.f; }
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                const F2 v = *reinterpret_cast<const F2*>(As + (lrow + j) * CA + 2 * cp);
+                fir_scatter<H0, NGV, HL>(j, v, a.v0, lo);
+                fir_scatter<H1, NGV, HL>(j, v, a.v1s, hi);
+            }
+            if (ocol < a.out_cols) {
+                float* dst = a.lolo + ((int64_t)bz * a.out_rows + orow) * a.out_cols + ocol;
+#pragma unroll
+                for (int i = 0; i < NOUT; ++i)
+                    if (orow + i < a.out_rows) *reinterpret_cast<F2*>(dst + (int64_t)i * a.out_cols) = lo[i];
+            }
+            store_q2c(a, hi, bz, orow / 2, ocol / 2, 0, 5);      // vertical high x horizontal low
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i) { lo[i].x = lo[i].y = 0.f; hi[i].x = hi[i].y = 0.f; }
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                const F2 v = *reinterpret_cast<const F2*>(Bs + (lrow + j) * CA + 2 * cp);
+                fir_scatter<H0, NGV, HL>(j, v, a.v0, lo);
+                fir_scatter<H1, NGV, HL>(j, v, a.v1, hi);
+            }
+            store_q2c(a, lo, bz, orow / 2, ocol / 2, 2, 3);      // vertical low x horizontal high
+            store_q2c(a, hi, bz, orow / 2, ocol / 2, 1, 4);      // high x high
+        }
+    }
+
+    template <int PH>
+    static DTCWT_D void phase(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        if (PH == 0) phase_load(a, sm, bx, by, bz, tid);
+        if (PH == 1) phase_patch_rows(a, sm, bx, by, bz, tid);
+        if (PH == 2) phase_patch_cols(a, sm, bx, by, bz, tid);
+        if (PH == 3) phase_rows(a, sm, bx, by, bz, tid);
+        if (PH == 4) phase_cols(a, sm, bx, by, bz, tid);
+    }
+};
+
+// =============================================================================== inverse level
+struct Inv2dArgs {
+    const float* z;                 // lowpass [n][rows][cols]
+    const float* yh;                // complex planar sub-bands [n][6][rows/2][cols/2] (strides below)
+    float* out;                     // [n][out_rows][out_cols]
+    int n, rows, cols;
+    int crop_r, crop_c;             // 1: drop the first and last output row / column (transform2d.py:263-268)
+    int out_rows, out_cols;         // P*rows/Q - 2*crop_r, ...
+    int64_t zs_n, zs_band, zs_row;
+    float gain[6];                  // gain_mask column of this level, times 1/sqrt2
+    PhaseTaps g0, g1;
+};
+
+template <class G0, class G1, int GH_, int GW_, int NGV_>
+struct Inv2d {
+    typedef Inv2dArgs Args;
+    static constexpr int P = G0::P, Q = G0::Q;
+    static constexpr int GH = GH_, GW = GW_, NGV = NGV_;
+    static constexpr int NGH = 4 / Q;
+    static constexpr int HL = cmax(spec_lo<G0>(), spec_lo<G1>());
+    static constexpr int HR = cmax(spec_hi<G0>(), spec_hi<G1>());
+    static constexpr int HLR = round_up(HL, 2), HRR = round_up(HR, 2);   // rows: whole quads
+    static constexpr int HLA = round_up(HL, 4), HRA = round_up(HR, 4);   // columns: whole float4
+    static constexpr int RI = Q * GH + HLR + HRR;
+    static constexpr int CI = Q * GW + HLA + HRA;
+    static constexpr int CP = P * GW;
+    static constexpr int WN = 4 + HLA + HRA;
+    static constexpr int NSEG = GW / NGH;
+    static constexpr int NR = Q * NGV + HLR + HRR;
+    static constexpr int NOUT = P * NGV;
+    static constexpr int kSmemFloats = 2 * RI * CI + 2 * RI * CP;
+    static constexpr int kThreads = kFusedThreads;
+    static constexpr int kPhases = 5;
+    static_assert(P == G1::P && Q == G1::Q, "filter pair must share its rate");
+    static_assert(((Q * GH) % 2) == 0 && ((Q * GW) % 4) == 0 && (GH % NGV) == 0 && (GW % NGH) == 0, "tile shape");
+    static_assert((P * NGH) % 4 == 0, "row task writes float4s");
+
+    static DTCWT_HD int tiles_r(const Args& a) { return (a.rows + Q * GH - 1) / (Q * GH); }
+    static DTCWT_HD int tiles_c(const Args& a) { return (a.cols + Q * GW - 1) / (Q * GW); }
+
+    // c2q (transform2d.py:324-350): gains are pre-scaled by 1/sqrt2
+    static DTCWT_D void c2q_quad(const Args& a, const float* zb, int64_t e, int band0, int band1,
+                                 float& A, float& B, float& C, float& D) {
+        const F2 w0 = *reinterpret_cast<const F2*>(zb + 2 * (band0 * a.zs_band + e));
+        const F2 w1 = *reinterpret_cast<const F2*>(zb + 2 * (band1 * a.zs_band + e));
+        const float g0 = a.gain[band0], g1 = a.gain[band1];
+        const float r0 = w0.x * g0, i0 = w0.y * g0, r1 = w1.x * g1, i1 = w1.y * g1;
+        A = r0 + r1; B = i0 + i1; C = i0 - i1; D = r1 - r0;
+    }
+
+    // phases 0 / 2: load one half of the inputs as real 2x2 quads, symmetric extension at quad granularity
+    //   HALF 0: in0 = Z,               in1 = c2q(bands 2,3)  (vertical low  x horizontal high)
+    //   HALF 1: in0 = c2q(bands 0,5),  in1 = c2q(bands 1,4)
+    template <int HALF>
+    static DTCWT_D void phase_load(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        float* in0 = sm;
+        float* in1 = sm + RI * CI;
+        constexpr int RQ = RI / 2, CQ = CI / 2;
+        const int qr0 = (Q * GH * by - HLR) / 2, qc0 = (Q * GW * bx - HLA) / 2;   // exact: all terms even
+        const int hq = a.rows / 2, wq = a.cols / 2;
+        const float* zimg = a.z + (int64_t)bz * a.rows * a.cols;
+        const float* zb = a.yh + 2 * (int64_t)bz * a.zs_n;
+        for (int task = tid; task < RQ * CQ; task += kThreads) {
+            const int qi = task / CQ, qj = task - qi * CQ;
+            int gi = qr0 + qi, gj = qc0 + qj;
+            bool fr = false, fc = false;
+            if (gi < 0) { gi = -1 - gi; fr = true; } else if (gi >= hq) { gi = 2 * hq - 1 - gi; fr = true; }
+            if (gj < 0) { gj = -1 - gj; fc = true; } else if (gj >= wq) { gj = 2 * wq - 1 - gj; fc = true; }
+            float A0 = 0.f, B0 = 0.f, C0 = 0.f, D0 = 0.f, A1 = 0.f, B1 = 0.f, C1 = 0.f, D1 = 0.f;
+            if (gi >= 0 && gi < hq && gj >= 0 && gj < wq) {
+                const int64_t e = (int64_t)gi * a.zs_row + gj;
+                if (HALF == 0) {
+                    const F2 t0 = *reinterpret_cast<const F2*>(zimg + (int64_t)(2 * gi) * a.cols + 2 * gj);
+                    const F2 t1 = *reinterpret_cast<const F2*>(zimg + (int64_t)(2 * gi + 1) * a.cols + 2 * gj);
+                    A0 = t0.x; B0 = t0.y; C0 = t1.x; D0 = t1.y;
+                    c2q_quad(a, zb, e, 2, 3, A1, B1, C1, D1);
+                } else {
+                    c2q_quad(a, zb, e, 0, 5, A0, B0, C0, D0);
+                    c2q_quad(a, zb, e, 1, 4, A1, B1, C1, D1);
+                }
+            }
+            if (fr) { float t; t = A0; A0 = C0; C0 = t; t = B0; B0 = D0; D0 = t; t = A1; A1 = C1; C1 = t; t = B1; B1 = D1; D1 = t; }
+            if (fc) { float t; t = A0; A0 = B0; B0 = t; t = C0; C0 = D0; D0 = t; t = A1; A1 = B1; B1 = t; t = C1; C1 = D1; D1 = t; }
+            F2 v;
+            v.x = A0; v.y = B0; *reinterpret_cast<F2*>(in0 + (2 * qi) * CI + 2 * qj) = v;
+            v.x = C0; v.y = D0; *reinterpret_cast<F2*>(in0 + (2 * qi + 1) * CI + 2 * qj) = v;
+            v.x = A1; v.y = B1; *reinterpret_cast<F2*>(in1 + (2 * qi) * CI + 2 * qj) = v;
+            v.x = C1; v.y = D1; *reinterpret_cast<F2*>(in1 + (2 * qi + 1) * CI + 2 * qj) = v;
+        }
+    }
+
+    // phases 1 / 3: row pass p[HALF] = H:g0(in0) + H:g1(in1)
+    template <int HALF>
+    static DTCWT_D void phase_rows(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        const float* in0 = sm;
+        const float* in1 = sm + RI * CI;
+        float* p = sm + 2 * RI * CI + HALF * RI * CP;
+        for (int task = tid; task < RI * NSEG; task += kThreads) {
+            const int lr = task / NSEG, seg = task - lr * NSEG;
+            float acc[P * NGH];
+#pragma unroll
+            for (int i = 0; i < P * NGH; ++i) acc[i] = 0.f;
+            float w[WN];
+            {
+                const F4* src = reinterpret_cast<const F4*>(in0 + lr * CI + seg * 4);
+#pragma unroll
+                for (int c = 0; c < WN / 4; ++c) {
+                    const F4 v = src[c];
+                    w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+                }
+                fir_gather<G0, NGH, HLA, WN>(w, a.g0, acc);
+            }
+            {
+                const F4* src = reinterpret_cast<const F4*>(in1 + lr * CI + seg * 4);
+#pragma unroll
+                for (int c = 0; c < WN / 4; ++c) {
+                    const F4 v = src[c];
+                    w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+                }
+                fir_gather<G1, NGH, HLA, WN>(w, a.g1, acc);
+            }
+            F4* dst = reinterpret_cast<F4*>(p + lr * CP + seg * (P * NGH));
+#pragma unroll
+            for (int c = 0; c < (P * NGH) / 4; ++c) {
+                F4 v;
+                v.x = acc[4 * c]; v.y = acc[4 * c + 1]; v.z = acc[4 * c + 2]; v.w = acc[4 * c + 3];
+                dst[c] = v;
+            }
+        }
+    }
+
+    // phase 4: column pass out = V:g0(p1) + V:g1(p2), cropped, stored from registers
+    static DTCWT_D void phase_cols(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        const float* p1 = sm + 2 * RI * CI;
+        const float* p2 = p1 + RI * CP;
+        for (int task = tid; task < (CP / 2) * (GH / NGV); task += kThreads) {
+            const int strip = task / (CP / 2), cp = task - strip * (CP / 2);
+            const int lrow = Q * NGV * strip;
+            F2 acc[NOUT];
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i) acc[i].x = acc[i].y = 0.f;
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                if (fir_row_used<G0, NGV, HLR>(j)) {
+                    const F2 v = *reinterpret_cast<const F2*>(p1 + (lrow + j) * CP + 2 * cp);
+                    fir_scatter<G0, NGV, HLR>(j, v, a.g0, acc);
+                }
+                if (fir_row_used<G1, NGV, HLR>(j)) {
+                    const F2 v = *reinterpret_cast<const F2*>(p2 + (lrow + j) * CP + 2 * cp);
+                    fir_scatter<G1, NGV, HLR>(j, v, a.g1, acc);
+                }
+            }
+            const int orow = P * (GH * by + NGV * strip) - a.crop_r;
+            const int ocol = P * GW * bx + 2 * cp - a.crop_c;
+            float* dst = a.out + (int64_t)bz * a.out_rows * a.out_cols;
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i) {
+                const int r = orow + i;
+                if (r < 0 || r >= a.out_rows) continue;
+                float* d = dst + (int64_t)r * a.out_cols + ocol;
+                if (a.crop_c == 0) {
+                    if (ocol < a.out_cols) *reinterpret_cast<F2*>(d) = acc[i];
+                } else {
+                    if (ocol >= 0 && ocol < a.out_cols) d[0] = acc[i].x;
+                    if (ocol + 1 < a.out_cols) d[1] = acc[i].y;
+                }
+            }
+        }
+    }
+
+    template <int PH>
+    static DTCWT_D void phase(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        if (PH == 0) phase_load<0>(a, sm, bx, by, bz, tid);
+        if (PH == 1) phase_rows<0>(a, sm, bx, by, bz, tid);
+        if (PH == 2) phase_load<1>(a, sm, bx, by, bz, tid);
+        if (PH == 3) phase_rows<1>(a, sm, bx, by, bz, tid);
+        if (PH == 4) phase_cols(a, sm, bx, by, bz, tid);
+    }
+};
+
+}  // namespace dtcwt

@@ -1,0 +1,151 @@
+// Device-side launch of the fused 2-D kernels: TMA staging of the forward input tile,
+// phase sequencing, dynamic shared memory opt-in.  Device build only.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "fused2d.cuh"
+
+namespace dtcwt {
+
+// ------------------------------------------------------------------ TMA / mbarrier (PTX)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// box [1][rows][cols] of a [n][rows][cols] tensor -> dense smem tile; out-of-range elements arrive as zeros
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <class K, int PH>
+struct PhaseRunner {
+    static __device__ __forceinline__ void run(const typename K::Args& a, float* sm, int bx, int by, int bz, int tid) {
+        K::template phase<PH>(a, sm, bx, by, bz, tid);
+        if (PH + 1 < K::kPhases) {
+            __syncthreads();
+            PhaseRunner<K, PH + 1>::run(a, sm, bx, by, bz, tid);
+        }
+    }
+};
+template <class K>
+struct PhaseRunner<K, 5> {
+    static __device__ __forceinline__ void run(const typename K::Args&, float*, int, int, int, int) {}
+};
+
+extern __shared__ __align__(128) float fused_smem[];
+
+template <class K>
+__global__ void __launch_bounds__(kFusedThreads, 2)
+fwd2d_kernel(const __grid_constant__ typename K::Args a, const __grid_constant__ CUtensorMap tmap) {
+    __shared__ __align__(8) uint64_t bar;
+    const int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z, tid = threadIdx.x;
+    if (a.use_tma) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bar, (uint32_t)(K::RX * K::CX * sizeof(float)));
+            tma_load_3d(fused_smem, &tmap, K::col0(bx) - a.pc_lo, K::row0(by) - a.pr_lo, bz, &bar);
+        }
+        uint32_t spins = 0;
+        while (!mbar_try_wait(&bar, 0)) {
+            if (++spins > (1u << 26)) __trap();      // a lost transaction must not hang the GPU
+        }
+    }
+    PhaseRunner<K, 0>::run(a, fused_smem, bx, by, bz, tid);
+}
+
+template <class K>
+__global__ void __launch_bounds__(kFusedThreads, 2) inv2d_kernel(const __grid_constant__ typename K::Args a) {
+    PhaseRunner<K, 0>::run(a, fused_smem, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                           const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                           CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                           CUtensorMapFloatOOBfill);
+
+static TensorMapEncodeTiledFn tensor_map_encoder() {
+    static TensorMapEncodeTiledFn fn = []() -> TensorMapEncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (TensorMapEncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+static bool tma_disabled_by_env() {
+    static const bool off = []() {
+        const char* e = getenv("DTCWT_B200_NO_TMA");
+        return e && e[0] && e[0] != '0';
+    }();
+    return off;
+}
+
+template <class K>
+static int launch_fwd2d(typename K::Args& a, void* stream) {
+    const size_t smem = (size_t)K::kSmemFloats * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(fwd2d_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    a.use_tma = 0;
+    // TMA needs a 16-byte aligned base and row pitch; other shapes take the plain-load staging phase
+    if (!tma_disabled_by_env() && (a.cols % 4) == 0 && ((uintptr_t)a.x % 16) == 0 && tensor_map_encoder()) {
+        const cuuint64_t dims[3] = {(cuuint64_t)a.cols, (cuuint64_t)a.rows, (cuuint64_t)(a.n > 0 ? a.n : 1)};
+        const cuuint64_t strides[2] = {(cuuint64_t)a.cols * 4, (cuuint64_t)a.cols * a.rows * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)K::CX, (cuuint32_t)K::RX, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = tensor_map_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.x, dims, strides, box,
+                                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) a.use_tma = 1;
+    }
+    if (a.n == 0) return DTCWT_B200_OK;
+    const dim3 grid((unsigned)K::tiles_c(a), (unsigned)K::tiles_r(a), (unsigned)a.n);
+    fwd2d_kernel<K><<<grid, kFusedThreads, smem, (cudaStream_t)stream>>>(a, map);
+    return (int)cudaGetLastError();
+}
+
+template <class K>
+static int launch_inv2d(typename K::Args& a, void* stream) {
+    const size_t smem = (size_t)K::kSmemFloats * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(inv2d_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    if (a.n == 0) return DTCWT_B200_OK;
+    const dim3 grid((unsigned)K::tiles_c(a), (unsigned)K::tiles_r(a), (unsigned)a.n);
+    inv2d_kernel<K><<<grid, kFusedThreads, smem, (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace dtcwt

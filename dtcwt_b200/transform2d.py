@@ -178,6 +178,10 @@ class Transform2d(object):
     def _fwd_level1(self, X, t, ph, pw):
         """Level 1 (reference :112-130): undecimated biort filters, vertical axis first."""
         N = X.shape[0]
+        if t["h2o"] is None:
+            fused = _ops.fwd2d_level1(X, t["h0o"], t["h1o"], (ph, pw))
+            if fused is not None:
+                return fused
         Lo = _ops.colfilter(X, t["h0o"], 1, (0, ph))
         Hi = _ops.colfilter(X, t["h1o"], 1, (0, ph))
         LoLo = _ops.colfilter(Lo, t["h0o"], 2, (0, pw))
@@ -196,6 +200,10 @@ class Transform2d(object):
         N, r, c = LoLo.shape
         pr = (1, 1) if r % 4 else (0, 0)
         pc = (1, 1) if c % 4 else (0, 0)
+        if t["h2a"] is None:
+            fused = _ops.fwd2d_levelq(LoLo, t["h0b"], t["h0a"], t["h1b"], t["h1a"], (pr[0], pc[0]))
+            if fused is not None:
+                return fused
         Lo = _ops.coldfilt(LoLo, t["h0b"], t["h0a"], 1, pr)
         Hi = _ops.coldfilt(LoLo, t["h1b"], t["h1a"], 1, pr)
         out = _ops.coldfilt(Lo, t["h0b"], t["h0a"], 2, pc)
@@ -242,6 +250,10 @@ class Transform2d(object):
             else:
                 raise ValueError("Sizes of highpasses are not valid for DTWAVEIFM2")
         cr, cc = crops
+        if t["g2a"] is None:
+            fused = _ops.inv2d_levelq(Z, yh, t["g0b"], t["g0a"], t["g1b"], t["g1a"], g, (cr, cc))
+            if fused is not None:
+                return fused
         lh = _ops.c2q(yh, _BANDS_HL[0], _BANDS_HL[1], g[0], g[5])
         hl = _ops.c2q(yh, _BANDS_LH[0], _BANDS_LH[1], g[2], g[3])
         hh = _ops.c2q(yh, _BANDS_HH[0], _BANDS_HH[1], g[1], g[4])
@@ -260,6 +272,10 @@ class Transform2d(object):
 
     def _inv_level1(self, Z, yh, t, g):
         self._check_lowpass(Z, yh)
+        if t["g2o"] is None:
+            fused = _ops.inv2d_level1(Z, yh, t["g0o"], t["g1o"], g)
+            if fused is not None:
+                return fused
         lh = _ops.c2q(yh, _BANDS_HL[0], _BANDS_HL[1], g[0], g[5])
         hl = _ops.c2q(yh, _BANDS_LH[0], _BANDS_LH[1], g[2], g[3])
         hh = _ops.c2q(yh, _BANDS_HH[0], _BANDS_HH[1], g[1], g[4])

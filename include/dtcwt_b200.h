@@ -132,6 +132,52 @@ int dtcwt_b200_c2cube_f64(const double *z, double *y, int64_t n, int64_t a, int6
                           int64_t zs_n, int64_t zs_chan, int64_t zs_0, int64_t zs_1, int64_t zs_2,
                           int chan0, void *stream);
 
+/* ---- fused per-level 2-D transform (float32) -----------------------------------
+ * One launch per pyramid level: the separable filtering and the q2c / c2q packing
+ * of a whole level happen in shared memory / registers; every input sample is read
+ * from HBM once and every output written once.
+ *
+ *   fwd2d_level1  replaces level 1 of Transform2d.forward  (numpy/transform2d.py:112-130)
+ *   fwd2d_levelq  replaces levels >= 2 of Transform2d.forward (:132-160)
+ *   inv2d_levelq  replaces levels >= 2 of Transform2d.inverse (:240-273)
+ *   inv2d_level1  replaces level 1 of Transform2d.inverse  (:275-293)
+ *
+ * x / z are real [n][rows][cols] (C-contiguous); lolo / out are C-contiguous real
+ * outputs; yh is the complex sub-band array of that level, element (b, band, i, j)
+ * at yh + 2*(b*zs_n + band*zs_band + i*zs_row + j) -- unit column stride, e.g. the
+ * planar [n][6][h][w] layout.
+ *   level1: lolo is [n][rows+pad_r_hi][cols+pad_c_hi], sub-bands half that size;
+ *           pad_*_hi = 1 repeats the last row / column of an odd-sized image (:86-94).
+ *   levelq: pad_r / pad_c = 1 extends that axis by one replicated sample on EACH side
+ *           (:134-140); lolo is [n][(rows+2*pad_r)/2][(cols+2*pad_c)/2].
+ *           (lo_a, lo_b), (hi_a, hi_b) are coldfilt's / colifilt's (ha, hb) arguments:
+ *           the reference passes (h0b, h0a), (h1b, h1a) forward and (g0b, g0a),
+ *           (g1b, g1a) inverse.
+ *   inverse: z is [n][rows][cols] with rows, cols twice the sub-band size; gain[6] is
+ *           the level's gain_mask column (:214-217, :243-245); crop_* = 1 drops the
+ *           first and last output row / column (:263-268).  out is
+ *           [n][2*rows-2*crop_r][2*cols-2*crop_c] (levelq) or [n][rows][cols] (level1).
+ * Returns DTCWT_B200_EUNSUPPORTED for requests the fused kernels do not cover (sides
+ * shorter than 32, tap counts other than odd <= 19 (level1) / 10, 14, 18 (levelq),
+ * q-shift pairs whose lowpass (highpass) tap correlation is not positive (negative));
+ * callers then compose the level from the primitives above.  Rows whose pitch is a
+ * multiple of 16 bytes are staged by TMA; set DTCWT_B200_NO_TMA=1 to force plain loads.
+ */
+int dtcwt_b200_fwd2d_level1_f32(const float *x, float *lolo, float *yh, int64_t n, int64_t rows, int64_t cols,
+                                int pad_r_hi, int pad_c_hi, const double *h0o, int m0, const double *h1o, int m1,
+                                int64_t zs_n, int64_t zs_band, int64_t zs_row, void *stream);
+int dtcwt_b200_fwd2d_levelq_f32(const float *x, float *lolo, float *yh, int64_t n, int64_t rows, int64_t cols,
+                                int pad_r, int pad_c, const double *lo_a, const double *lo_b, const double *hi_a,
+                                const double *hi_b, int m, int64_t zs_n, int64_t zs_band, int64_t zs_row,
+                                void *stream);
+int dtcwt_b200_inv2d_levelq_f32(const float *z, const float *yh, float *out, int64_t n, int64_t rows, int64_t cols,
+                                int crop_r, int crop_c, const double *lo_a, const double *lo_b, const double *hi_a,
+                                const double *hi_b, int m, const double *gain, int64_t zs_n, int64_t zs_band,
+                                int64_t zs_row, void *stream);
+int dtcwt_b200_inv2d_level1_f32(const float *z, const float *yh, float *out, int64_t n, int64_t rows, int64_t cols,
+                                const double *g0o, int m0, const double *g1o, int m1, const double *gain,
+                                int64_t zs_n, int64_t zs_band, int64_t zs_row, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

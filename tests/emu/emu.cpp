@@ -11,7 +11,12 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+
+#include <vector>
+
 #include "../../dtcwt_b200/csrc/generic_kernels.cuh"
+#include "../../dtcwt_b200/csrc/fused2d.cuh"
 
 namespace dtcwt {
 
@@ -22,9 +27,46 @@ static int launch_1d(const typename Elem::Args& a, void* /*stream*/) {
     return DTCWT_B200_OK;
 }
 
+// A fused kernel is a sequence of phases separated by block barriers: run every phase for every
+// thread of a block before the next one, block by block.  Shared memory is a scratch vector filled
+// with NaN so that a read of something no phase wrote shows up in the results.
+template <class K, int PH>
+struct EmuPhases {
+    static void run(const typename K::Args& a, float* sm, int bx, int by, int bz) {
+        for (int tid = 0; tid < K::kThreads; ++tid) K::template phase<PH>(a, sm, bx, by, bz, tid);
+        EmuPhases<K, PH + 1>::run(a, sm, bx, by, bz);
+    }
+};
+template <class K>
+struct EmuPhases<K, 5> {
+    static void run(const typename K::Args&, float*, int, int, int) {}
+};
+
+template <class K>
+static int emu_launch(typename K::Args& a) {
+    static_assert(K::kPhases == 5, "phase count");
+    std::vector<float> sm(K::kSmemFloats);
+    for (int bz = 0; bz < a.n; ++bz)
+        for (int by = 0; by < K::tiles_r(a); ++by)
+            for (int bx = 0; bx < K::tiles_c(a); ++bx) {
+                for (size_t i = 0; i < sm.size(); ++i) sm[i] = NAN;
+                EmuPhases<K, 0>::run(a, sm.data(), bx, by, bz);
+            }
+    return DTCWT_B200_OK;
+}
+
+template <class K>
+static int launch_fwd2d(typename K::Args& a, void* /*stream*/) {
+    a.use_tma = 0;
+    return emu_launch<K>(a);
+}
+template <class K>
+static int launch_inv2d(typename K::Args& a, void* /*stream*/) { return emu_launch<K>(a); }
+
 }  // namespace dtcwt
 
 #include "../../dtcwt_b200/csrc/abi_generic.inl"
+#include "../../dtcwt_b200/csrc/abi_fused2d.inl"
 
 extern "C" {
 
