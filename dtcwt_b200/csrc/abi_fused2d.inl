@@ -54,12 +54,12 @@ static bool aligned_to(const void* p, size_t a) { return ((uintptr_t)p % a) == 0
 typedef Fwd2d<SpecCol<13>, SpecCol<19>, 64, 64, 8> FwdL1_13_19;     // near_sym_b (+ anything shorter, zero-padded)
 typedef Fwd2d<SpecCol<5>, SpecCol<7>, 64, 64, 8> FwdL1_5_7;         // near_sym_a (+ legall 5/3)
 typedef Fwd2d<SpecCol<19>, SpecCol<19>, 64, 64, 8> FwdL1_19_19;     // any odd pair up to 19 taps
-typedef Inv2d<SpecCol<19>, SpecCol<13>, 64, 64, 8> InvL1_19_13;
-typedef Inv2d<SpecCol<7>, SpecCol<5>, 64, 64, 8> InvL1_7_5;
-typedef Inv2d<SpecCol<19>, SpecCol<19>, 64, 64, 8> InvL1_19_19;
+typedef Inv2d<SpecCol<19>, SpecCol<13>, 16, 1, 4> InvL1_19_13;
+typedef Inv2d<SpecCol<7>, SpecCol<5>, 16, 1, 4> InvL1_7_5;
+typedef Inv2d<SpecCol<19>, SpecCol<19>, 16, 1, 4> InvL1_19_19;
 // levels >= 2: q-shift pairs; every shipped family has a positive lowpass and a negative highpass tap correlation
 template <int M> struct FwdLq { typedef Fwd2d<SpecDec<M, true>, SpecDec<M, false>, 32, 16, 2> type; };
-template <int M> struct InvLq { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 16, 16, 2> type; };
+template <int M> struct InvLq { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4> type; };
 
 static int fwd_common(Fwd2dArgs& a, const float* x, float* lolo, float* yh, int64_t n, int64_t rows, int64_t cols,
                       int pr_lo, int pr_hi, int pc_lo, int pc_hi, int P, int Q, int64_t zs_n, int64_t zs_band,
@@ -87,10 +87,14 @@ static int inv_common(Inv2dArgs& a, const float* z, const float* yh, float* out,
     if (n > 65535 || rows < kFusedMinSide || cols < kFusedMinSide || rows > (1 << 24) || cols > (1 << 24))
         return DTCWT_B200_EUNSUPPORTED;
     if (!aligned_to(z, 8) || !aligned_to(yh, 8) || !aligned_to(out, 8)) return DTCWT_B200_EUNSUPPORTED;
+    // the kernels index one image's lowpass / sub-bands with 32-bit element offsets
+    if (rows * cols >= (1LL << 30) || zs_band < 0 || zs_row < 0 || 6 * zs_band + (rows / 2) * zs_row + cols >= (1LL << 29))
+        return DTCWT_B200_EUNSUPPORTED;
     a.z = z; a.yh = yh; a.out = out;
     a.n = (int)n; a.rows = (int)rows; a.cols = (int)cols;
     a.crop_r = crop_r; a.crop_c = crop_c;
     a.out_rows = P * (int)rows / Q - 2 * crop_r; a.out_cols = P * (int)cols / Q - 2 * crop_c;
+    a.out_vec4 = (crop_c == 0 && (a.out_cols % 4) == 0 && aligned_to(out, 16)) ? 1 : 0;
     a.zs_n = zs_n; a.zs_band = zs_band; a.zs_row = zs_row;
     for (int b = 0; b < 6; ++b) a.gain[b] = (float)(gain[b] * kInvSqrt2);
     return DTCWT_B200_OK;

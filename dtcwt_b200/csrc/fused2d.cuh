@@ -46,6 +46,24 @@ struct PhaseTaps {
     float t[kMaxPhases][kMaxPhaseTaps];
 };
 
+// acc += c * v on a pair of floats.  sm_100a has a packed FP32 FMA (PTX fma.rn.f32x2, SASS FFMA2) whose
+// multiplier may be a scalar broadcast from a uniform register: one issue slot, two FMAs.
+DTCWT_D F2 fma2(const float c, const F2 v, const F2 acc) {
+#ifdef DTCWT_EMU
+    F2 r;
+    r.x = fmaf(c, v.x, acc.x);
+    r.y = fmaf(c, v.y, acc.y);
+    return r;
+#else
+    F2 cc = make_float2(c, c), r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(reinterpret_cast<unsigned long long&>(r))
+        : "l"(reinterpret_cast<const unsigned long long&>(cc)), "l"(reinterpret_cast<const unsigned long long&>(v)),
+          "l"(reinterpret_cast<const unsigned long long&>(acc)));
+    return r;
+#endif
+}
+
 DTCWT_HD constexpr int cmax(int a, int b) { return a > b ? a : b; }
 DTCWT_HD constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
@@ -110,9 +128,7 @@ DTCWT_D void fir_scatter(const int j, const F2 v, const PhaseTaps& t, F2 (&acc)[
         for (int ph = 0; ph < F::P; ++ph) {
             const int num = j - HALO - F::Q * ii - F::b(ph);
             if (num >= 0 && (num % F::S) == 0 && (num / F::S) < F::K) {
-                const float c = t.t[ph][num / F::S];
-                acc[F::P * ii + ph].x = fmaf(c, v.x, acc[F::P * ii + ph].x);
-                acc[F::P * ii + ph].y = fmaf(c, v.y, acc[F::P * ii + ph].y);
+                acc[F::P * ii + ph] = fma2(t.t[ph][num / F::S], v, acc[F::P * ii + ph]);
             }
         }
     }
@@ -161,6 +177,7 @@ struct Fwd2d {
     static constexpr int kSmemFloats = RX * CX + 2 * RX * CA;
     static constexpr int kThreads = kFusedThreads;
     static constexpr int kPhases = 5;
+    static constexpr int kMinBlocks = 2;
     static_assert(P == H1::P && Q == H1::Q, "filter pair must share its rate");
     static_assert((NOUT % 2) == 0 && (GH % NGV) == 0 && (GW % NGH) == 0 && (CA % 2) == 0, "tile shape");
     static_assert(P * NGH == 4 || P * NGH == 2, "row task writes a float4 or float2");
@@ -326,175 +343,223 @@ struct Inv2dArgs {
     int n, rows, cols;
     int crop_r, crop_c;             // 1: drop the first and last output row / column (transform2d.py:263-268)
     int out_rows, out_cols;         // P*rows/Q - 2*crop_r, ...
+    int out_vec4;                   // rows of `out` are 16-byte aligned and not cropped: float4 stores
     int64_t zs_n, zs_band, zs_row;
     float gain[6];                  // gain_mask column of this level, times 1/sqrt2
     PhaseTaps g0, g1;
 };
 
-template <class G0, class G1, int GH_, int GW_, int NGV_>
+// Column pass first: each thread owns one quad column (two adjacent real columns), NGV groups of rows
+// and ONE of the two intermediate images (its warp's role):
+//     role 0: y1 = V:g0(Z)  + V:g1(lh)        role 1: y2 = V:g0(hl) + V:g1(hh)   (transform2d.py:248-256, 279-285)
+// It walks down the quad rows its outputs depend on, loads the lowpass quad / the complex coefficients
+// straight from global memory (coalesced 8-byte loads, next quad row prefetched), applies c2q in
+// registers and scatters the real rows into its accumulators, which go to shared memory; the row pass
+// out = H:g0(y1) + H:g1(y2) reads them back with a register window and stores float4s.
+// No input staging, one block barrier.  Tiles whose halo lies inside the image take a variant compiled
+// without the symmetric-extension logic.
+template <class G0, class G1, int NGV_, int NSTRIP_, int NWIDE_>
 struct Inv2d {
     typedef Inv2dArgs Args;
     static constexpr int P = G0::P, Q = G0::Q;
-    static constexpr int GH = GH_, GW = GW_, NGV = NGV_;
+    static constexpr int NGV = NGV_, NSTRIP = NSTRIP_, NWIDE = NWIDE_;
     static constexpr int NGH = 4 / Q;
     static constexpr int HL = cmax(spec_lo<G0>(), spec_lo<G1>());
     static constexpr int HR = cmax(spec_hi<G0>(), spec_hi<G1>());
     static constexpr int HLR = round_up(HL, 2), HRR = round_up(HR, 2);   // rows: whole quads
-    static constexpr int HLA = round_up(HL, 4), HRA = round_up(HR, 4);   // columns: whole float4
-    static constexpr int RI = Q * GH + HLR + HRR;
-    static constexpr int CI = Q * GW + HLA + HRA;
-    static constexpr int CP = P * GW;
-    static constexpr int WN = 4 + HLA + HRA;
-    static constexpr int NSEG = GW / NGH;
-    static constexpr int NR = Q * NGV + HLR + HRR;
-    static constexpr int NOUT = P * NGV;
-    static constexpr int kSmemFloats = 2 * RI * CI + 2 * RI * CP;
+    static constexpr int HLC = round_up(HL, 2), HRC = round_up(HR, 2);   // columns: whole quads
     static constexpr int kThreads = kFusedThreads;
-    static constexpr int kPhases = 5;
+    static constexpr int QCOLS = 32 * NWIDE;                             // quad columns of a tile (whole warps)
+    static constexpr int CY = 2 * QCOLS;                                 // columns of y1 / y2 in smem
+    static constexpr int TWI = (CY - HLC - HRC) / 4 * 4;                 // input columns a tile produces (multiple of 4)
+    static constexpr int GH = NGV * NSTRIP;                              // row groups of a tile
+    static constexpr int RY = P * GH;                                    // rows of y1 / y2
+    static constexpr int NQR = (Q * NGV + HLR + HRR) / 2;                // quad rows a column task reads
+    static constexpr int NOUT = P * NGV;
+    static constexpr int WN = round_up(HLC + 4 + HR, 4);                 // register window of a row task
+    static constexpr int NSEG = TWI / 4;
+    static constexpr int kSmemFloats = 2 * RY * CY;
+    static constexpr int kPhases = 2;
+    static constexpr int kMinBlocks = 3;                                 // register budget: 3 CTAs (24 warps) per SM
     static_assert(P == G1::P && Q == G1::Q, "filter pair must share its rate");
-    static_assert(((Q * GH) % 2) == 0 && ((Q * GW) % 4) == 0 && (GH % NGV) == 0 && (GW % NGH) == 0, "tile shape");
-    static_assert((P * NGH) % 4 == 0, "row task writes float4s");
+    static_assert(2 * NSTRIP * NWIDE * 32 == kThreads && ((Q * NGV) % 2) == 0 && (P * NGH) % 4 == 0, "tile shape");
+    static_assert(WN + 4 * (NSEG - 1) <= CY, "row-pass window must stay inside the smem row");
 
     static DTCWT_HD int tiles_r(const Args& a) { return (a.rows + Q * GH - 1) / (Q * GH); }
-    static DTCWT_HD int tiles_c(const Args& a) { return (a.cols + Q * GW - 1) / (Q * GW); }
+    static DTCWT_HD int tiles_c(const Args& a) { return (a.cols + TWI - 1) / TWI; }
 
-    // c2q (transform2d.py:324-350): gains are pre-scaled by 1/sqrt2
-    static DTCWT_D void c2q_quad(const Args& a, const float* zb, int64_t e, int band0, int band1,
-                                 float& A, float& B, float& C, float& D) {
-        const F2 w0 = *reinterpret_cast<const F2*>(zb + 2 * (band0 * a.zs_band + e));
-        const F2 w1 = *reinterpret_cast<const F2*>(zb + 2 * (band1 * a.zs_band + e));
-        const float g0 = a.gain[band0], g1 = a.gain[band1];
-        const float r0 = w0.x * g0, i0 = w0.y * g0, r1 = w1.x * g1, i1 = w1.y * g1;
-        A = r0 + r1; B = i0 + i1; C = i0 - i1; D = r1 - r0;
+    struct Raw { F2 v[4]; };       // role 0: Z top row, Z bottom row, band 0, band 5;  role 1: bands 2, 3, 1, 4
+
+    static DTCWT_HD int reflect_quad(int g, int n, bool& flip) {
+        flip = false;
+        if (g < 0) { g = -1 - g; flip = true; } else if (g >= n) { g = 2 * n - 1 - g; flip = true; }
+        return g;
     }
 
-    // phases 0 / 2: load one half of the inputs as real 2x2 quads, symmetric extension at quad granularity
-    //   HALF 0: in0 = Z,               in1 = c2q(bands 2,3)  (vertical low  x horizontal high)
-    //   HALF 1: in0 = c2q(bands 0,5),  in1 = c2q(bands 1,4)
-    template <int HALF>
-    static DTCWT_D void phase_load(const Args& a, float* sm, int bx, int by, int bz, int tid) {
-        float* in0 = sm;
-        float* in1 = sm + RI * CI;
-        constexpr int RQ = RI / 2, CQ = CI / 2;
-        const int qr0 = (Q * GH * by - HLR) / 2, qc0 = (Q * GW * bx - HLA) / 2;   // exact: all terms even
-        const int hq = a.rows / 2, wq = a.cols / 2;
-        const float* zimg = a.z + (int64_t)bz * a.rows * a.cols;
-        const float* zb = a.yh + 2 * (int64_t)bz * a.zs_n;
-        for (int task = tid; task < RQ * CQ; task += kThreads) {
-            const int qi = task / CQ, qj = task - qi * CQ;
-            int gi = qr0 + qi, gj = qc0 + qj;
-            bool fr = false, fc = false;
-            if (gi < 0) { gi = -1 - gi; fr = true; } else if (gi >= hq) { gi = 2 * hq - 1 - gi; fr = true; }
-            if (gj < 0) { gj = -1 - gj; fc = true; } else if (gj >= wq) { gj = 2 * wq - 1 - gj; fc = true; }
-            float A0 = 0.f, B0 = 0.f, C0 = 0.f, D0 = 0.f, A1 = 0.f, B1 = 0.f, C1 = 0.f, D1 = 0.f;
-            if (gi >= 0 && gi < hq && gj >= 0 && gj < wq) {
-                const int64_t e = (int64_t)gi * a.zs_row + gj;
-                if (HALF == 0) {
-                    const F2 t0 = *reinterpret_cast<const F2*>(zimg + (int64_t)(2 * gi) * a.cols + 2 * gj);
-                    const F2 t1 = *reinterpret_cast<const F2*>(zimg + (int64_t)(2 * gi + 1) * a.cols + 2 * gj);
-                    A0 = t0.x; B0 = t0.y; C0 = t1.x; D0 = t1.y;
-                    c2q_quad(a, zb, e, 2, 3, A1, B1, C1, D1);
-                } else {
-                    c2q_quad(a, zb, e, 0, 5, A0, B0, C0, D0);
-                    c2q_quad(a, zb, e, 1, 4, A1, B1, C1, D1);
-                }
-            }
-            if (fr) { float t; t = A0; A0 = C0; C0 = t; t = B0; B0 = D0; D0 = t; t = A1; A1 = C1; C1 = t; t = B1; B1 = D1; D1 = t; }
-            if (fc) { float t; t = A0; A0 = B0; B0 = t; t = C0; C0 = D0; D0 = t; t = A1; A1 = B1; B1 = t; t = C1; C1 = D1; D1 = t; }
-            F2 v;
-            v.x = A0; v.y = B0; *reinterpret_cast<F2*>(in0 + (2 * qi) * CI + 2 * qj) = v;
-            v.x = C0; v.y = D0; *reinterpret_cast<F2*>(in0 + (2 * qi + 1) * CI + 2 * qj) = v;
-            v.x = A1; v.y = B1; *reinterpret_cast<F2*>(in1 + (2 * qi) * CI + 2 * qj) = v;
-            v.x = C1; v.y = D1; *reinterpret_cast<F2*>(in1 + (2 * qi + 1) * CI + 2 * qj) = v;
+    template <int ROLE, bool EDGE>
+    static DTCWT_D void load_quad_row(const Args& a, const float* zimg, const float* zb, int qrow, int gj, bool okc,
+                                      Raw& r) {
+        int gi = qrow;
+        bool ok = true;
+        if (EDGE) {
+            bool fr;
+            gi = reflect_quad(qrow, a.rows / 2, fr);
+            ok = okc && gi >= 0 && gi < a.rows / 2;
+        }
+        if (EDGE && !ok) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r.v[i].x = r.v[i].y = 0.f;
+            return;
+        }
+        const int e = gi * (int)a.zs_row + gj;                  // the ABI guarantees 32-bit element offsets
+        if (ROLE == 0) {
+            const int ez = 2 * gi * a.cols + 2 * gj;
+            r.v[0] = *reinterpret_cast<const F2*>(zimg + ez);
+            r.v[1] = *reinterpret_cast<const F2*>(zimg + ez + a.cols);
+            r.v[2] = *reinterpret_cast<const F2*>(zb + 2 * e);
+            r.v[3] = *reinterpret_cast<const F2*>(zb + 2 * (e + 5 * (int)a.zs_band));
+        } else {
+            r.v[0] = *reinterpret_cast<const F2*>(zb + 2 * (e + 2 * (int)a.zs_band));
+            r.v[1] = *reinterpret_cast<const F2*>(zb + 2 * (e + 3 * (int)a.zs_band));
+            r.v[2] = *reinterpret_cast<const F2*>(zb + 2 * (e + 1 * (int)a.zs_band));
+            r.v[3] = *reinterpret_cast<const F2*>(zb + 2 * (e + 4 * (int)a.zs_band));
         }
     }
 
-    // phases 1 / 3: row pass p[HALF] = H:g0(in0) + H:g1(in1)
-    template <int HALF>
+    // c2q (transform2d.py:324-350), gains pre-scaled by 1/sqrt2:  top row (A, B), bottom row (C, D)
+    static DTCWT_D void c2q_rows(const F2 w0, const F2 w1, float g0, float g1, F2& top, F2& bot) {
+        const float r0 = w0.x * g0, i0 = w0.y * g0;
+        top.x = fmaf(w1.x, g1, r0); top.y = fmaf(w1.y, g1, i0);
+        bot.x = fmaf(-w1.y, g1, i0); bot.y = fmaf(w1.x, g1, -r0);
+    }
+    // symmetric extension at quad granularity: a mirrored quad has its rows and / or columns exchanged
+    static DTCWT_D void flip_quad(bool fr, bool fc, F2& top, F2& bot) {
+        if (fc) { float t; t = top.x; top.x = top.y; top.y = t; t = bot.x; bot.x = bot.y; bot.y = t; }
+        if (fr) { const F2 t = top; top = bot; bot = t; }
+    }
+
+    template <int ROLE, bool EDGE>
+    static DTCWT_D void cols_body(const Args& a, float* sm, int bx, int by, int bz, int qc, int strip) {
+        int gj = (TWI * bx - HLC) / 2 + qc;                      // exact: TWI and HLC are even
+        bool fc = false, okc = true;
+        if (EDGE) {
+            gj = reflect_quad(gj, a.cols / 2, fc);
+            okc = gj >= 0 && gj < a.cols / 2;
+        }
+        const int qr0 = (Q * (GH * by + NGV * strip) - HLR) / 2;
+        const float* zimg = a.z + (int64_t)bz * a.rows * a.cols;
+        const float* zb = a.yh + 2 * (int64_t)bz * a.zs_n;
+        const float ga0 = a.gain[ROLE == 0 ? 0 : 2], ga1 = a.gain[ROLE == 0 ? 5 : 3];
+        const float gb0 = a.gain[1], gb1 = a.gain[4];
+        F2 acc[NOUT];
+#pragma unroll
+        for (int i = 0; i < NOUT; ++i) acc[i].x = acc[i].y = 0.f;
+        Raw cur, nxt;
+        load_quad_row<ROLE, EDGE>(a, zimg, zb, qr0, gj, okc, cur);
+#pragma unroll
+        for (int jq = 0; jq < NQR; ++jq) {
+            if (jq + 1 < NQR) load_quad_row<ROLE, EDGE>(a, zimg, zb, qr0 + jq + 1, gj, okc, nxt);
+            F2 at, ab, bt, bb;         // image A (filtered with g0) and image B (g1): top / bottom real rows
+            if (ROLE == 0) {
+                at = cur.v[0]; ab = cur.v[1];
+                c2q_rows(cur.v[2], cur.v[3], ga0, ga1, bt, bb);
+            } else {
+                c2q_rows(cur.v[0], cur.v[1], ga0, ga1, at, ab);
+                c2q_rows(cur.v[2], cur.v[3], gb0, gb1, bt, bb);
+            }
+            if (EDGE) {
+                bool fr;
+                reflect_quad(qr0 + jq, a.rows / 2, fr);
+                flip_quad(fr, fc, at, ab);
+                flip_quad(fr, fc, bt, bb);
+            }
+            fir_scatter<G0, NGV, HLR>(2 * jq, at, a.g0, acc);
+            fir_scatter<G1, NGV, HLR>(2 * jq, bt, a.g1, acc);
+            fir_scatter<G0, NGV, HLR>(2 * jq + 1, ab, a.g0, acc);
+            fir_scatter<G1, NGV, HLR>(2 * jq + 1, bb, a.g1, acc);
+            cur = nxt;
+        }
+        float* y = sm + ROLE * RY * CY + (NOUT * strip) * CY + 2 * qc;
+#pragma unroll
+        for (int i = 0; i < NOUT; ++i) *reinterpret_cast<F2*>(y + i * CY) = acc[i];
+    }
+
+    // phase 0: column pass from global memory into y1 / y2
+    static DTCWT_D void phase_cols(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        const int qc = tid % QCOLS;
+        const int t = tid / QCOLS;
+        const int role = t % 2, strip = t / 2;                   // uniform within a warp
+        const bool edge = (Q * GH * by - HLR < 0) || (Q * GH * (by + 1) + HRR > a.rows) ||
+                          (TWI * bx - HLC < 0) || (TWI * bx - HLC + CY > a.cols);
+        if (role == 0) {
+            if (edge) cols_body<0, true>(a, sm, bx, by, bz, qc, strip);
+            else cols_body<0, false>(a, sm, bx, by, bz, qc, strip);
+        } else {
+            if (edge) cols_body<1, true>(a, sm, bx, by, bz, qc, strip);
+            else cols_body<1, false>(a, sm, bx, by, bz, qc, strip);
+        }
+    }
+
+    // phase 1: row pass out = H:g0(y1) + H:g1(y2); one task = one output row x 4 input columns
     static DTCWT_D void phase_rows(const Args& a, float* sm, int bx, int by, int bz, int tid) {
-        const float* in0 = sm;
-        const float* in1 = sm + RI * CI;
-        float* p = sm + 2 * RI * CI + HALF * RI * CP;
-        for (int task = tid; task < RI * NSEG; task += kThreads) {
+        const float* y1 = sm;
+        const float* y2 = sm + RY * CY;
+        float* img = a.out + (int64_t)bz * a.out_rows * a.out_cols;
+        for (int task = tid; task < RY * NSEG; task += kThreads) {
             const int lr = task / NSEG, seg = task - lr * NSEG;
+            const int r = P * GH * by + lr - a.crop_r;
+            if (r < 0 || r >= a.out_rows) continue;
             float acc[P * NGH];
 #pragma unroll
             for (int i = 0; i < P * NGH; ++i) acc[i] = 0.f;
             float w[WN];
             {
-                const F4* src = reinterpret_cast<const F4*>(in0 + lr * CI + seg * 4);
+                const F4* src = reinterpret_cast<const F4*>(y1 + lr * CY + seg * 4);
 #pragma unroll
                 for (int c = 0; c < WN / 4; ++c) {
                     const F4 v = src[c];
                     w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
                 }
-                fir_gather<G0, NGH, HLA, WN>(w, a.g0, acc);
+                fir_gather<G0, NGH, HLC, WN>(w, a.g0, acc);
             }
             {
-                const F4* src = reinterpret_cast<const F4*>(in1 + lr * CI + seg * 4);
+                const F4* src = reinterpret_cast<const F4*>(y2 + lr * CY + seg * 4);
 #pragma unroll
                 for (int c = 0; c < WN / 4; ++c) {
                     const F4 v = src[c];
                     w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
                 }
-                fir_gather<G1, NGH, HLA, WN>(w, a.g1, acc);
+                fir_gather<G1, NGH, HLC, WN>(w, a.g1, acc);
             }
-            F4* dst = reinterpret_cast<F4*>(p + lr * CP + seg * (P * NGH));
+            const int c0 = (P / Q) * (TWI * bx + 4 * seg) - a.crop_c;     // first output column of the task
+            float* d = img + (int64_t)r * a.out_cols + c0;
+            if (a.out_vec4 && c0 + P * NGH <= a.out_cols) {                // 16-byte aligned rows, no crop
 #pragma unroll
-            for (int c = 0; c < (P * NGH) / 4; ++c) {
-                F4 v;
-                v.x = acc[4 * c]; v.y = acc[4 * c + 1]; v.z = acc[4 * c + 2]; v.w = acc[4 * c + 3];
-                dst[c] = v;
-            }
-        }
-    }
-
-    // phase 4: column pass out = V:g0(p1) + V:g1(p2), cropped, stored from registers
-    static DTCWT_D void phase_cols(const Args& a, float* sm, int bx, int by, int bz, int tid) {
-        const float* p1 = sm + 2 * RI * CI;
-        const float* p2 = p1 + RI * CP;
-        for (int task = tid; task < (CP / 2) * (GH / NGV); task += kThreads) {
-            const int strip = task / (CP / 2), cp = task - strip * (CP / 2);
-            const int lrow = Q * NGV * strip;
-            F2 acc[NOUT];
-#pragma unroll
-            for (int i = 0; i < NOUT; ++i) acc[i].x = acc[i].y = 0.f;
-#pragma unroll
-            for (int j = 0; j < NR; ++j) {
-                if (fir_row_used<G0, NGV, HLR>(j)) {
-                    const F2 v = *reinterpret_cast<const F2*>(p1 + (lrow + j) * CP + 2 * cp);
-                    fir_scatter<G0, NGV, HLR>(j, v, a.g0, acc);
+                for (int c = 0; c < (P * NGH) / 4; ++c) {
+                    F4 v;
+                    v.x = acc[4 * c]; v.y = acc[4 * c + 1]; v.z = acc[4 * c + 2]; v.w = acc[4 * c + 3];
+                    reinterpret_cast<F4*>(d)[c] = v;
                 }
-                if (fir_row_used<G1, NGV, HLR>(j)) {
-                    const F2 v = *reinterpret_cast<const F2*>(p2 + (lrow + j) * CP + 2 * cp);
-                    fir_scatter<G1, NGV, HLR>(j, v, a.g1, acc);
-                }
-            }
-            const int orow = P * (GH * by + NGV * strip) - a.crop_r;
-            const int ocol = P * GW * bx + 2 * cp - a.crop_c;
-            float* dst = a.out + (int64_t)bz * a.out_rows * a.out_cols;
+            } else if (a.crop_c == 0) {                                    // rows are 8-byte aligned
 #pragma unroll
-            for (int i = 0; i < NOUT; ++i) {
-                const int r = orow + i;
-                if (r < 0 || r >= a.out_rows) continue;
-                float* d = dst + (int64_t)r * a.out_cols + ocol;
-                if (a.crop_c == 0) {
-                    if (ocol < a.out_cols) *reinterpret_cast<F2*>(d) = acc[i];
-                } else {
-                    if (ocol >= 0 && ocol < a.out_cols) d[0] = acc[i].x;
-                    if (ocol + 1 < a.out_cols) d[1] = acc[i].y;
-                }
+                for (int i = 0; i < P * NGH; i += 2)
+                    if (c0 + i < a.out_cols) {
+                        F2 v;
+                        v.x = acc[i]; v.y = acc[i + 1];
+                        *reinterpret_cast<F2*>(d + i) = v;
+                    }
+            } else {
+#pragma unroll
+                for (int i = 0; i < P * NGH; ++i)
+                    if (c0 + i >= 0 && c0 + i < a.out_cols) d[i] = acc[i];
             }
         }
     }
 
     template <int PH>
     static DTCWT_D void phase(const Args& a, float* sm, int bx, int by, int bz, int tid) {
-        if (PH == 0) phase_load<0>(a, sm, bx, by, bz, tid);
-        if (PH == 1) phase_rows<0>(a, sm, bx, by, bz, tid);
-        if (PH == 2) phase_load<1>(a, sm, bx, by, bz, tid);
-        if (PH == 3) phase_rows<1>(a, sm, bx, by, bz, tid);
-        if (PH == 4) phase_cols(a, sm, bx, by, bz, tid);
+        if (PH == 0) phase_cols(a, sm, bx, by, bz, tid);
+        if (PH == 1) phase_rows(a, sm, bx, by, bz, tid);
     }
 };
 

@@ -41,25 +41,23 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
         : "memory");
 }
 
-template <class K, int PH>
+template <class K, int PH, bool DONE = (PH >= K::kPhases)>
 struct PhaseRunner {
     static __device__ __forceinline__ void run(const typename K::Args& a, float* sm, int bx, int by, int bz, int tid) {
+        if (PH > 0) __syncthreads();
         K::template phase<PH>(a, sm, bx, by, bz, tid);
-        if (PH + 1 < K::kPhases) {
-            __syncthreads();
-            PhaseRunner<K, PH + 1>::run(a, sm, bx, by, bz, tid);
-        }
+        PhaseRunner<K, PH + 1>::run(a, sm, bx, by, bz, tid);
     }
 };
-template <class K>
-struct PhaseRunner<K, 5> {
+template <class K, int PH>
+struct PhaseRunner<K, PH, true> {
     static __device__ __forceinline__ void run(const typename K::Args&, float*, int, int, int, int) {}
 };
 
 extern __shared__ __align__(128) float fused_smem[];
 
 template <class K>
-__global__ void __launch_bounds__(kFusedThreads, 2)
+__global__ void __launch_bounds__(kFusedThreads, K::kMinBlocks)
 fwd2d_kernel(const __grid_constant__ typename K::Args a, const __grid_constant__ CUtensorMap tmap) {
     __shared__ __align__(8) uint64_t bar;
     const int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z, tid = threadIdx.x;
@@ -82,7 +80,7 @@ fwd2d_kernel(const __grid_constant__ typename K::Args a, const __grid_constant__
 }
 
 template <class K>
-__global__ void __launch_bounds__(kFusedThreads, 2) inv2d_kernel(const __grid_constant__ typename K::Args a) {
+__global__ void __launch_bounds__(kFusedThreads, K::kMinBlocks) inv2d_kernel(const __grid_constant__ typename K::Args a) {
     PhaseRunner<K, 0>::run(a, fused_smem, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
 }
 

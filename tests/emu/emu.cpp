@@ -30,21 +30,20 @@ static int launch_1d(const typename Elem::Args& a, void* /*stream*/) {
 // A fused kernel is a sequence of phases separated by block barriers: run every phase for every
 // thread of a block before the next one, block by block.  Shared memory is a scratch vector filled
 // with NaN so that a read of something no phase wrote shows up in the results.
-template <class K, int PH>
+template <class K, int PH, bool DONE = (PH >= K::kPhases)>
 struct EmuPhases {
     static void run(const typename K::Args& a, float* sm, int bx, int by, int bz) {
         for (int tid = 0; tid < K::kThreads; ++tid) K::template phase<PH>(a, sm, bx, by, bz, tid);
         EmuPhases<K, PH + 1>::run(a, sm, bx, by, bz);
     }
 };
-template <class K>
-struct EmuPhases<K, 5> {
+template <class K, int PH>
+struct EmuPhases<K, PH, true> {
     static void run(const typename K::Args&, float*, int, int, int) {}
 };
 
 template <class K>
 static int emu_launch(typename K::Args& a) {
-    static_assert(K::kPhases == 5, "phase count");
     std::vector<float> sm(K::kSmemFloats);
     for (int bz = 0; bz < a.n; ++bz)
         for (int by = 0; by < K::tiles_r(a); ++by)

@@ -71,6 +71,7 @@ def check_roundtrip(X, biort, qshift, nlevels, gain=None, expect_fused=True):
     ((65, 131), 2),       # odd sizes: last row / column repeated (transform2d.py:86-94)
     ((160, 136), 3),      # three levels, level 3 input 40x34 (pad columns)
     ((32, 32), 1),        # smallest image the fused kernels accept
+    ((64, 1056), 2),      # wide enough for interior (no symmetric-extension) tiles of every kernel
 ])
 def test_fused_vs_oracle_shapes(backend, shape, nlevels):
     rs = np.random.RandomState(shape[0] * 1000 + shape[1])
