@@ -49,14 +49,56 @@ static void taps_int(PhaseTaps& t, const double* ha, const double* hb, int m, bo
 
 static bool aligned_to(const void* p, size_t a) { return ((uintptr_t)p % a) == 0; }
 
+// Streaming kernels (stream2d.cuh): reversed, centred taps as for taps_col; returns the mask of non-zero taps.
+static uint32_t taps_col_s(ColTaps& t, const double* h, int m, int K, double scale) {
+    for (int k = 0; k < kStreamMaxTaps; ++k) t.t[k] = 0.f;
+    const int z = (K - m) / 2;
+    uint32_t mask = 0;
+    for (int k = 0; k < m; ++k) {
+        const float v = (float)((double)(float)h[k] * scale);
+        t.t[z + (m - 1 - k)] = v;
+        if (v != 0.f) mask |= 1u << (z + (m - 1 - k));
+    }
+    return mask;
+}
+static void pair_tab(PairTab& p, const ColTaps& t, int K) {
+    for (int k = 0; k <= kStreamMaxTaps; ++k) {
+        p.p[k].x = (k < K) ? t.t[k] : 0.f;
+        p.p[k].y = (k >= 1 && k - 1 < K) ? t.t[k - 1] : 0.f;
+    }
+}
+static int env_int(const char* name, int dflt) {      // tuning experiments only
+    const char* e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
+// Emitting periods per run: enough runs to fill the GPU several times over (148 SMs x 2 CTAs), but runs long
+// enough that the one warm-up period stays a few per cent of the work.
+static int choose_periods(int rows, int ring, int64_t strips_times_n) {
+    const int total = (rows + ring - 1) / ring;
+    int64_t runs = (4 * 296 + strips_times_n - 1) / (strips_times_n > 0 ? strips_times_n : 1);
+    if (runs < 1) runs = 1;
+    int per = (int)((total + runs - 1) / runs);
+    if (per < 16) per = 16;
+    if (per > total) per = total;
+    return per;
+}
+
 // ------------------------------------------------------------------ kernel instances
 // level 1: (lowpass taps, highpass taps) of the shipped biorthogonal families, longest first
-typedef Fwd2d<SpecCol<13>, SpecCol<19>, 64, 64, 8> FwdL1_13_19;     // near_sym_b (+ anything shorter, zero-padded)
-typedef Fwd2d<SpecCol<5>, SpecCol<7>, 64, 64, 8> FwdL1_5_7;         // near_sym_a (+ legall 5/3)
-typedef Fwd2d<SpecCol<19>, SpecCol<19>, 64, 64, 8> FwdL1_19_19;     // any odd pair up to 19 taps
-typedef Inv2d<SpecCol<19>, SpecCol<13>, 16, 1, 4> InvL1_19_13;
-typedef Inv2d<SpecCol<7>, SpecCol<5>, 16, 1, 4> InvL1_7_5;
-typedef Inv2d<SpecCol<19>, SpecCol<19>, 16, 1, 4> InvL1_19_19;
+// level-1 forward: tile kernels (TMA-staged tile, packed row pass into shared memory, column pass from shared memory)
+constexpr uint32_t kMask19 = 0x7ffffu & ~(1u << 1) & ~(1u << 17);    // near_sym_b: taps 1 and m-2 are exactly zero
+constexpr uint32_t kMask13 = 0x1fffu & ~(1u << 1) & ~(1u << 11);
+typedef Fwd2d<SpecCol<13, kMask13>, SpecCol<19, kMask19>, 64, 64, 8> FwdT1_nsb;    // near_sym_b: exact-zero taps compiled out
+typedef Fwd2d<SpecCol<5>, SpecCol<7>, 64, 64, 8> FwdT1_5_7;                         // near_sym_a (+ legall 5/3)
+typedef Fwd2d<SpecCol<19>, SpecCol<19>, 64, 64, 8> FwdT1_19_19;                     // any odd pair up to 19 taps
+// level-1 forward: streaming kernels, selected with DTCWT_B200_FWD_STREAM=1 (h0 taps, h1 taps, masks of taps that may be non-zero, ring)
+typedef FwdS1<13, 19, kMask13, kMask19, 20, 192, 3, BakedTaps<NearSymB_h0>, BakedTaps<NearSymB_h1s>, BakedTaps<NearSymB_h1> > FwdL1_nsb;
+typedef FwdS1<19, 19, 0x7ffffu, 0x7ffffu, 20, 192, 2> FwdL1_19_19;          // any odd pair up to 19 taps (zero-padded)
+typedef FwdS1<5, 7, 0x1fu, 0x7fu, 8, 192, 3> FwdL1_5_7;                     // near_sym_a (+ legall 5/3)
+// level-1 inverse: streaming kernels (g0 taps, g1 taps, masks of taps that may be non-zero, ring, prefetch depth)
+typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1> > InvL1_nsb;   // near_sym_b, taps as immediates
+typedef InvS1<19, 19, 0x7ffffu, 0x7ffffu, 24, 3> InvL1_19_19;       // any odd pair up to 19 taps (zero-padded)
+typedef InvS1<7, 5, 0x7fu, 0x1fu, 8, 2> InvL1_7_5;                  // near_sym_a (+ legall 3/5)
 // levels >= 2: q-shift pairs; every shipped family has a positive lowpass and a negative highpass tap correlation
 template <int M> struct FwdLq { typedef Fwd2d<SpecDec<M, true>, SpecDec<M, false>, 32, 16, 2> type; };
 template <int M> struct InvLq { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4> type; };
@@ -113,19 +155,55 @@ int dtcwt_b200_fwd2d_level1_f32(const float* x, float* lolo, float* yh, int64_t 
     if (!h0o || !h1o || m0 < 1 || m1 < 1 || pad_r_hi < 0 || pad_r_hi > 1 || pad_c_hi < 0 || pad_c_hi > 1)
         return DTCWT_B200_EINVAL;
     if (!(m0 & 1) || !(m1 & 1) || m0 > 19 || m1 > 19) return DTCWT_B200_EUNSUPPORTED;
-    Fwd2dArgs a;
-    const int rc = fwd_common(a, x, lolo, yh, n, rows, cols, 0, pad_r_hi, 0, pad_c_hi, 1, 1, zs_n, zs_band, zs_row);
+    Fwd2dArgs c;                      // argument checks shared with the q-shift levels
+    const int rc = fwd_common(c, x, lolo, yh, n, rows, cols, 0, pad_r_hi, 0, pad_c_hi, 1, 1, zs_n, zs_band, zs_row);
     if (rc) return rc;
-    const int K0 = (m0 <= 5 && m1 <= 7) ? 5 : (m0 <= 13 ? 13 : 19);
-    const int K1 = (K0 == 5) ? 7 : 19;
-    taps_col(a.h0, h0o, m0, K0, 1.0);
-    taps_col(a.h1s, h1o, m1, K1, kInvSqrt2);
-    taps_col(a.v0, h0o, m0, K0, 1.0);
-    taps_col(a.v1, h1o, m1, K1, 1.0);
-    taps_col(a.v1s, h1o, m1, K1, kInvSqrt2);
-    if (K0 == 5) return launch_fwd2d<FwdL1_5_7>(a, stream);
-    if (K0 == 13) return launch_fwd2d<FwdL1_13_19>(a, stream);
-    return launch_fwd2d<FwdL1_19_19>(a, stream);
+    FwdS1Args a;
+    a.x = x; a.lolo = lolo; a.yh = yh;
+    a.n = c.n; a.rows = c.rows; a.cols = c.cols; a.Lr = c.Lr; a.Lc = c.Lc;
+    a.zs_n = zs_n; a.zs_band = zs_band; a.zs_row = zs_row;
+    a.use_tma = 0;
+    const bool small = (m0 <= 5 && m1 <= 7);
+    const int K1 = small ? 7 : 19;
+    const int K0 = small ? 5 : ((m0 <= 13 && m1 > m0) ? 13 : 19);
+    ColTaps t0, t1s;
+    uint32_t nz0 = taps_col_s(t0, h0o, m0, K0, 1.0);
+    const uint32_t nz1 = taps_col_s(t1s, h1o, m1, K1, kInvSqrt2);
+    taps_col_s(a.v1, h1o, m1, K1, 1.0);
+    const bool nsb = !small && K0 == 13 && BakedTaps<NearSymB_h0>::same(t0) && BakedTaps<NearSymB_h1s>::same(t1s) &&
+                     BakedTaps<NearSymB_h1>::same(a.v1);
+    if (!small && K0 == 13 && !nsb) nz0 = taps_col_s(t0, h0o, m0, 19, 1.0);      // general instance: two 19-slot filters
+    const int K0e = (small || nsb) ? K0 : 19;
+    pair_tab(a.ph0, t0, K0e);
+    pair_tab(a.ph1s, t1s, K1);
+    a.v0 = t0;
+    a.v1s = t1s;
+    if (!env_int("DTCWT_B200_FWD_STREAM", 0)) {
+        // default: the tile kernel (measured faster than the streaming one for the forward direction, profiles/)
+        const int KT0 = small ? 5 : (nsb ? 13 : 19);
+        taps_col(c.h0, h0o, m0, KT0, 1.0);
+        taps_col(c.h1s, h1o, m1, K1, kInvSqrt2);
+        taps_col(c.v0, h0o, m0, KT0, 1.0);
+        taps_col(c.v1, h1o, m1, K1, 1.0);
+        taps_col(c.v1s, h1o, m1, K1, kInvSqrt2);
+        ColTaps r0;
+        taps_col_s(r0, h0o, m0, KT0, 1.0);
+        pair_tab(c.ph0, r0, KT0);
+        pair_tab(c.ph1s, t1s, K1);
+        if (small) return launch_fwd2d<FwdT1_5_7>(c, stream);
+        if (nsb) return launch_fwd2d<FwdT1_nsb>(c, stream);
+        return launch_fwd2d<FwdT1_19_19>(c, stream);
+    }
+    if (small) {
+        a.periods = choose_periods(a.Lr, FwdL1_5_7::RING, (int64_t)FwdL1_5_7::tiles_c(a) * a.n);
+        return launch_fwds1<FwdL1_5_7>(a, stream);
+    }
+    if (nsb) {
+        a.periods = choose_periods(a.Lr, FwdL1_nsb::RING, (int64_t)FwdL1_nsb::tiles_c(a) * a.n);
+        return launch_fwds1<FwdL1_nsb>(a, stream);
+    }
+    a.periods = choose_periods(a.Lr, FwdL1_19_19::RING, (int64_t)FwdL1_19_19::tiles_c(a) * a.n);
+    return launch_fwds1<FwdL1_19_19>(a, stream);
 }
 
 // transform2d.py:132-160 (levels >= 2 of Transform2d.forward), 8-tuple qshift.  (lo_a, lo_b) and (hi_a, hi_b) are
@@ -177,16 +255,37 @@ int dtcwt_b200_inv2d_level1_f32(const float* z, const float* yh, float* out, int
                                 int64_t zs_n, int64_t zs_band, int64_t zs_row, void* stream) {
     if (!g0o || !g1o || m0 < 1 || m1 < 1) return DTCWT_B200_EINVAL;
     if (!(m0 & 1) || !(m1 & 1) || m0 > 19 || m1 > 19) return DTCWT_B200_EUNSUPPORTED;
-    Inv2dArgs a;
-    const int rc = inv_common(a, z, yh, out, n, rows, cols, 0, 0, 1, 1, gain, zs_n, zs_band, zs_row);
+    Inv2dArgs c;                      // argument checks shared with the q-shift levels
+    const int rc = inv_common(c, z, yh, out, n, rows, cols, 0, 0, 1, 1, gain, zs_n, zs_band, zs_row);
     if (rc) return rc;
-    const int K1 = (m0 <= 7 && m1 <= 5) ? 5 : (m1 <= 13 ? 13 : 19);
-    const int K0 = (K1 == 5) ? 7 : 19;
-    taps_col(a.g0, g0o, m0, K0, 1.0);
-    taps_col(a.g1, g1o, m1, K1, 1.0);
-    if (K1 == 5) return launch_inv2d<InvL1_7_5>(a, stream);
-    if (K1 == 13) return launch_inv2d<InvL1_19_13>(a, stream);
-    return launch_inv2d<InvL1_19_19>(a, stream);
+    if (cols >= (1 << 27) || zs_row >= (1 << 27)) return DTCWT_B200_EUNSUPPORTED;   // byte strides are 32-bit
+    InvS1Args a;
+    a.z = z; a.yh = yh; a.out = out;
+    a.n = c.n; a.rows = c.rows; a.cols = c.cols;
+    a.out_vec4 = ((a.cols % 4) == 0 && aligned_to(out, 16)) ? 1 : 0;
+    a.zs_n = zs_n; a.zs_band = zs_band; a.zs_row = zs_row;
+    for (int b = 0; b < 6; ++b) a.gain[b] = c.gain[b];
+    const bool small = (m0 <= 7 && m1 <= 5);
+    const int K0 = small ? 7 : 19;
+    const int K1 = small ? 5 : ((m1 <= 13 && m0 > m1) ? 13 : 19);
+    const uint32_t nz0 = taps_col_s(a.g0, g0o, m0, K0, 1.0);
+    const uint32_t nz1 = taps_col_s(a.g1, g1o, m1, K1, 1.0);
+    pair_tab(a.p0, a.g0, K0);
+    pair_tab(a.p1, a.g1, K1);
+    if (small) {
+        a.periods = choose_periods(a.rows, InvL1_7_5::RING, (int64_t)InvL1_7_5::tiles_c(a) * a.n);
+        return launch_invs1<InvL1_7_5>(a, stream);
+    }
+    if (K1 == 13 && BakedTaps<NearSymB_g0>::same(a.g0) && BakedTaps<NearSymB_g1>::same(a.g1)) {
+        a.periods = choose_periods(a.rows, InvL1_nsb::RING, (int64_t)InvL1_nsb::tiles_c(a) * a.n);
+        return launch_invs1<InvL1_nsb>(a, stream);
+    }
+    if (K1 == 13) {                  // the general instance takes two 19-slot filters
+        taps_col_s(a.g1, g1o, m1, 19, 1.0);
+        pair_tab(a.p1, a.g1, 19);
+    }
+    a.periods = choose_periods(a.rows, InvL1_19_19::RING, (int64_t)InvL1_19_19::tiles_c(a) * a.n);
+    return launch_invs1<InvL1_19_19>(a, stream);
 }
 
 }  // extern "C"

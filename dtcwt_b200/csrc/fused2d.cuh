@@ -26,6 +26,8 @@
 // The bodies are split into phases separated by block barriers; tests/emu runs
 // the same phases thread by thread on the host (DTCWT_EMU).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace dtcwt {
@@ -67,17 +69,48 @@ DTCWT_D F2 fma2(const float c, const F2 v, const F2 acc) {
 DTCWT_HD constexpr int cmax(int a, int b) { return a > b ? a : b; }
 DTCWT_HD constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+// ------------------------------------------------------------------ packed-FMA helpers shared with stream2d.cuh
+constexpr int kStreamThreads = 256;
+constexpr int kStreamMaxTaps = 19;
+
+struct ColTaps { float t[kStreamMaxTaps]; };           // t[k'] = h[m-1-k'] centred in K slots (taps_col)
+struct PairTab { F2 p[kStreamMaxTaps + 1]; };          // p[k] = (t[k], t[k-1]), k = 0..K; t[-1] = t[K] = 0
+
+DTCWT_D F2 zero2() { F2 z; z.x = 0.f; z.y = 0.f; return z; }
+DTCWT_HD constexpr uint32_t full_mask(int K) { return (K >= 32) ? 0xffffffffu : ((1u << K) - 1u); }
+DTCWT_HD constexpr bool tap_on(uint32_t mask, int k, int K) { return k >= 0 && k < K && ((mask >> k) & 1u); }
+DTCWT_HD constexpr int pmod(int a, int m) { return ((a % m) + m) % m; }
+
+// Row pass over a register window: w holds NW consecutive samples, sample j of the window sits at
+// output-relative column j + W0 (output 0 of the task is column 0), filter centre C, acc[e/2] holds outputs
+// (e, e+1).  out[e] += t[k] w[j] with k = j + W0 - e + C.
+template <int K, uint32_t MASK, int C, int W0, int NOUT, int NW>
+DTCWT_D void pair_gather4(const int j0, const F4 v, const PairTab& pt, F2 (&acc)[NOUT / 2]) {
+    const float w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int ep = 0; ep < NOUT / 2; ++ep) {
+            const int k = j0 + i + W0 - 2 * ep + C;       // tap of output 2ep; output 2ep+1 takes tap k-1
+            if (k >= 0 && k <= K && (tap_on(MASK, k, K) || tap_on(MASK, k - 1, K))) acc[ep] = fma2(w[i], pt.p[k], acc[ep]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ filter structure
-template <int K_>
-struct SpecCol {                       // colfilter, K odd (shorter filters are zero-padded, centred)
+template <int K_, uint32_t MASK_ = 0xffffffffu>
+struct SpecCol {                       // colfilter, K odd (shorter filters are zero-padded, centred); MASK: taps that may be non-zero
     static constexpr int P = 1, Q = 1, S = 1, K = K_;
+    static constexpr uint32_t MASK = MASK_ & full_mask(K_);
     static DTCWT_HD constexpr int b(int) { return -(K_ - 1) / 2; }
+    static DTCWT_HD constexpr bool on(int, int k) { return (MASK >> k) & 1u; }
 };
 
 template <int M, bool POS>
 struct SpecDec {                       // coldfilt: phase 0 is Ya (delta 0) when POS else Yb (delta 1)
     static constexpr int P = 2, Q = 4, S = 2, K = M;
     static DTCWT_HD constexpr int b(int ph) { return -M + 2 + (((ph == 0) == POS) ? 0 : 1); }
+    static DTCWT_HD constexpr bool on(int, int) { return true; }
 };
 
 template <int M, bool POS>
@@ -88,6 +121,7 @@ struct SpecInt {                       // colifilt (phase tables: abi_generic.in
                              : (POS ? ph - 2 : (ph == 0 ? -1 : ph == 1 ? -2 : ph == 2 ? 1 : 0));
     }
     static DTCWT_HD constexpr int b(int ph) { return -(M / 2) + 2 + off(ph); }
+    static DTCWT_HD constexpr bool on(int, int) { return true; }
 };
 
 template <class F>
@@ -112,7 +146,8 @@ DTCWT_D void fir_gather(const float (&w)[WN], const PhaseTaps& t, float (&acc)[F
         for (int ph = 0; ph < F::P; ++ph) {
             float s = acc[F::P * ii + ph];
 #pragma unroll
-            for (int k = 0; k < F::K; ++k) s = fmaf(t.t[ph][k], w[F::Q * ii + F::b(ph) + F::S * k + HALO], s);
+            for (int k = 0; k < F::K; ++k)
+                if (F::on(ph, k)) s = fmaf(t.t[ph][k], w[F::Q * ii + F::b(ph) + F::S * k + HALO], s);
             acc[F::P * ii + ph] = s;
         }
     }
@@ -127,7 +162,7 @@ DTCWT_D void fir_scatter(const int j, const F2 v, const PhaseTaps& t, F2 (&acc)[
 #pragma unroll
         for (int ph = 0; ph < F::P; ++ph) {
             const int num = j - HALO - F::Q * ii - F::b(ph);
-            if (num >= 0 && (num % F::S) == 0 && (num / F::S) < F::K) {
+            if (num >= 0 && (num % F::S) == 0 && (num / F::S) < F::K && F::on(ph, num / F::S)) {
                 acc[F::P * ii + ph] = fma2(t.t[ph][num / F::S], v, acc[F::P * ii + ph]);
             }
         }
@@ -138,7 +173,7 @@ DTCWT_HD constexpr bool fir_row_used(const int j) {
     for (int ii = 0; ii < NG; ++ii)
         for (int ph = 0; ph < F::P; ++ph) {
             const int num = j - HALO - F::Q * ii - F::b(ph);
-            if (num >= 0 && (num % F::S) == 0 && (num / F::S) < F::K) return true;
+            if (num >= 0 && (num % F::S) == 0 && (num / F::S) < F::K && F::on(ph, num / F::S)) return true;
         }
     return false;
 }
@@ -156,6 +191,7 @@ struct Fwd2dArgs {
     int64_t zs_n, zs_band, zs_row;
     PhaseTaps h0, h1s;              // row pass: lowpass, highpass/sqrt2
     PhaseTaps v0, v1, v1s;          // column pass: lowpass, highpass, highpass/sqrt2
+    PairTab ph0, ph1s;              // level 1 only: the row-pass taps as pairs (t[k], t[k-1]) for the packed row pass
 };
 
 template <class H0, class H1, int GH_, int GW_, int NGV_>
@@ -232,8 +268,40 @@ struct Fwd2d {
         }
     }
 
+    // level 1 (P = Q = 1): scalar sample x tap pair (t[k], t[k-1]) accumulates the output pair (c, c+1) in one FFMA2
+    template <class HH = H0>
+    static DTCWT_D typename std::enable_if<HH::P == 1 && HH::Q == 1>::type phase_rows_packed(const Args& a, float* sm, int tid) {
+        const float* Xs = sm;
+        float* As = sm + RX * CX;
+        float* Bs = As + RX * CA;
+        constexpr int C0 = (H0::K - 1) / 2, C1 = (H1::K - 1) / 2;
+        for (int task = tid; task < RX * NSEG; task += kThreads) {
+            const int lr = task / NSEG, seg = task - lr * NSEG;
+            F2 oa[2], ob[2];
+            oa[0] = zero2(); oa[1] = zero2(); ob[0] = zero2(); ob[1] = zero2();
+            const F4* src = reinterpret_cast<const F4*>(Xs + lr * CX + seg * 4);
+#pragma unroll
+            for (int c = 0; c < WN / 4; ++c) {
+                const F4 v = src[c];
+                pair_gather4<H0::K, H0::MASK, C0, -HLA, 4, WN>(4 * c, v, a.ph0, oa);
+                pair_gather4<H1::K, H1::MASK, C1, -HLA, 4, WN>(4 * c, v, a.ph1s, ob);
+            }
+            F4 va, vb;
+            va.x = oa[0].x; va.y = oa[0].y; va.z = oa[1].x; va.w = oa[1].y;
+            vb.x = ob[0].x; vb.y = ob[0].y; vb.z = ob[1].x; vb.w = ob[1].y;
+            *reinterpret_cast<F4*>(As + lr * CA + seg * 4) = va;
+            *reinterpret_cast<F4*>(Bs + lr * CA + seg * 4) = vb;
+        }
+    }
+    template <class HH = H0>
+    static DTCWT_D typename std::enable_if<!(HH::P == 1 && HH::Q == 1)>::type phase_rows_packed(const Args&, float*, int) {}
+
     // phase 3: row pass, one task = one tile row x 4 input columns
     static DTCWT_D void phase_rows(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        if (P == 1 && Q == 1) {
+            phase_rows_packed(a, sm, tid);
+            return;
+        }
         const float* Xs = sm;
         float* As = sm + RX * CX;
         float* Bs = As + RX * CA;

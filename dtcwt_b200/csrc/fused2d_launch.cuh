@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "fused2d.cuh"
+#include "stream2d.cuh"
 
 namespace dtcwt {
 
@@ -84,6 +85,83 @@ __global__ void __launch_bounds__(kFusedThreads, K::kMinBlocks) inv2d_kernel(con
     PhaseRunner<K, 0>::run(a, fused_smem, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
 }
 
+// streaming level-1 inverse (stream2d.cuh): warm-up period, then column pass / row pass per period
+template <class K>
+__global__ void __launch_bounds__(kStreamThreads, K::kMinBlocks) invs1_kernel(const __grid_constant__ typename K::Args a) {
+    const int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z, tid = threadIdx.x;
+    typename K::Thread th;
+    K::init(a, th, bx, by, bz, tid);
+    const int np = K::run_periods(a, by);
+    for (int p = 0; p < np; ++p) {
+        K::cols(a, th, fused_smem, bx, by, bz, tid, p);
+        if (p > 0) {
+            __syncthreads();
+            K::rows(a, fused_smem, bx, by, bz, tid, p);
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();      // a lost transaction must not hang the GPU
+    }
+}
+
+// streaming level-1 forward (stream2d.cuh).  Input rows of period p+1 are fetched by TMA while period p computes:
+// two buffers, one mbarrier each.  Periods that reach above or below the image are staged with plain loads at
+// the symmetrically extended row indices instead (two or three periods per run of an image's first / last run).
+template <class K>
+__device__ __forceinline__ void fwds1_issue(const typename K::Args& a, float* sm, uint64_t* bar, const CUtensorMap* box,
+                                            int bx, int by, int bz, int p) {
+    fence_proxy_async_smem();
+    mbar_expect_tx(&bar[p & 1], (uint32_t)(K::XBUF * sizeof(float)));
+    tma_load_3d(sm + (p & 1) * K::XBUF, box, K::col_base(bx), K::row_base(a, by, p), bz, &bar[p & 1]);
+}
+
+template <class K>
+__global__ void __launch_bounds__(K::kThreads) __maxnreg__(K::kMaxRegs)
+fwds1_kernel(const __grid_constant__ typename K::Args a, const __grid_constant__ CUtensorMap tm_box) {
+    __shared__ __align__(8) uint64_t bar[2];
+    const int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z, tid = threadIdx.x;
+    typename K::Thread th;
+    K::init(th);
+    const int np = K::run_periods(a, by);
+    if (a.use_tma) {
+        if (tid == 0) {
+            mbar_init(&bar[0], 1);
+            mbar_init(&bar[1], 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (tid == 0 && K::rows_inside(a, by, 0)) fwds1_issue<K>(a, fused_smem, bar, &tm_box, bx, by, bz, 0);
+    }
+    const bool patch = !K::cols_inside(a, bx);
+    uint32_t phase = 0;                       // bit b: parity the next wait on bar[b] uses
+    for (int p = 0; p < np; ++p) {
+        const bool tma = a.use_tma && K::rows_inside(a, by, p);
+        if (a.use_tma && tid == 0 && p + 1 < np && K::rows_inside(a, by, p + 1))
+            fwds1_issue<K>(a, fused_smem, bar, &tm_box, bx, by, bz, p + 1);
+        if (tma) {
+            mbar_wait(&bar[p & 1], (phase >> (p & 1)) & 1u);
+            phase ^= 1u << (p & 1);
+            if (patch) {
+                K::patch_cols(a, fused_smem, bx, p, tid);
+                __syncthreads();
+            }
+        } else {
+            K::load_plain(a, fused_smem, bx, by, bz, p, tid);
+            __syncthreads();
+        }
+        K::rows(a, fused_smem, p, tid);
+        __syncthreads();
+        K::cols(a, th, fused_smem, bx, by, bz, tid, p);
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                            const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -143,6 +221,42 @@ static int launch_inv2d(typename K::Args& a, void* stream) {
     if (a.n == 0) return DTCWT_B200_OK;
     const dim3 grid((unsigned)K::tiles_c(a), (unsigned)K::tiles_r(a), (unsigned)a.n);
     inv2d_kernel<K><<<grid, kFusedThreads, smem, (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+template <class K>
+static int launch_fwds1(typename K::Args& a, void* stream) {
+    const size_t smem = (size_t)K::kSmemFloats * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(fwds1_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    CUtensorMap box;
+    memset(&box, 0, sizeof(box));
+    a.use_tma = 0;
+    // TMA needs a 16-byte aligned base and row pitch; other shapes are staged with plain loads
+    if (!tma_disabled_by_env() && (a.cols % 4) == 0 && ((uintptr_t)a.x % 16) == 0 && tensor_map_encoder()) {
+        const cuuint64_t dims[3] = {(cuuint64_t)a.cols, (cuuint64_t)a.rows, (cuuint64_t)(a.n > 0 ? a.n : 1)};
+        const cuuint64_t strides[2] = {(cuuint64_t)a.cols * 4, (cuuint64_t)a.cols * a.rows * 4};
+        const cuuint32_t bbox[3] = {(cuuint32_t)K::CXS, (cuuint32_t)K::RING, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = tensor_map_encoder()(&box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.x, dims, strides, bbox,
+                                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) a.use_tma = 1;
+    }
+    if (a.n == 0) return DTCWT_B200_OK;
+    const dim3 grid((unsigned)K::tiles_c(a), (unsigned)K::tiles_r(a), (unsigned)a.n);
+    fwds1_kernel<K><<<grid, K::kThreads, smem, (cudaStream_t)stream>>>(a, box);
+    return (int)cudaGetLastError();
+}
+
+template <class K>
+static int launch_invs1(typename K::Args& a, void* stream) {
+    const size_t smem = (size_t)K::kSmemFloats * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(invs1_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    if (a.n == 0) return DTCWT_B200_OK;
+    const dim3 grid((unsigned)K::tiles_c(a), (unsigned)K::tiles_r(a), (unsigned)a.n);
+    invs1_kernel<K><<<grid, kStreamThreads, smem, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
 

@@ -17,6 +17,7 @@
 
 #include "../../dtcwt_b200/csrc/generic_kernels.cuh"
 #include "../../dtcwt_b200/csrc/fused2d.cuh"
+#include "../../dtcwt_b200/csrc/stream2d.cuh"
 
 namespace dtcwt {
 
@@ -61,6 +62,47 @@ static int launch_fwd2d(typename K::Args& a, void* /*stream*/) {
 }
 template <class K>
 static int launch_inv2d(typename K::Args& a, void* /*stream*/) { return emu_launch<K>(a); }
+
+// Streaming kernels keep per-thread state (accumulator ring, prefetched rows) across barriers: one Thread
+// object per emulated thread, the period loop of the device kernel replayed with every thread run in turn.
+template <class K>
+static int launch_invs1(typename K::Args& a, void* /*stream*/) {
+    std::vector<float> sm(K::kSmemFloats);
+    std::vector<typename K::Thread> th(K::kThreads);
+    for (int bz = 0; bz < a.n; ++bz)
+        for (int by = 0; by < K::tiles_r(a); ++by)
+            for (int bx = 0; bx < K::tiles_c(a); ++bx) {
+                for (size_t i = 0; i < sm.size(); ++i) sm[i] = NAN;
+                for (int tid = 0; tid < K::kThreads; ++tid) K::init(a, th[tid], bx, by, bz, tid);
+                const int np = K::run_periods(a, by);
+                for (int p = 0; p < np; ++p) {
+                    for (int tid = 0; tid < K::kThreads; ++tid) K::cols(a, th[tid], sm.data(), bx, by, bz, tid, p);
+                    if (p > 0)
+                        for (int tid = 0; tid < K::kThreads; ++tid) K::rows(a, sm.data(), bx, by, bz, tid, p);
+                }
+            }
+    return DTCWT_B200_OK;
+}
+
+template <class K>
+static int launch_fwds1(typename K::Args& a, void* /*stream*/) {
+    std::vector<float> sm(K::kSmemFloats);
+    std::vector<typename K::Thread> th(K::kThreads);
+    a.use_tma = 0;
+    for (int bz = 0; bz < a.n; ++bz)
+        for (int by = 0; by < K::tiles_r(a); ++by)
+            for (int bx = 0; bx < K::tiles_c(a); ++bx) {
+                for (size_t i = 0; i < sm.size(); ++i) sm[i] = NAN;
+                for (int tid = 0; tid < K::kThreads; ++tid) K::init(th[tid]);
+                const int np = K::run_periods(a, by);
+                for (int p = 0; p < np; ++p) {
+                    for (int tid = 0; tid < K::kThreads; ++tid) K::load_plain(a, sm.data(), bx, by, bz, p, tid);
+                    for (int tid = 0; tid < K::kThreads; ++tid) K::rows(a, sm.data(), p, tid);
+                    for (int tid = 0; tid < K::kThreads; ++tid) K::cols(a, th[tid], sm.data(), bx, by, bz, tid, p);
+                }
+            }
+    return DTCWT_B200_OK;
+}
 
 }  // namespace dtcwt
 

@@ -72,6 +72,8 @@ def check_roundtrip(X, biort, qshift, nlevels, gain=None, expect_fused=True):
     ((160, 136), 3),      # three levels, level 3 input 40x34 (pad columns)
     ((32, 32), 1),        # smallest image the fused kernels accept
     ((64, 1056), 2),      # wide enough for interior (no symmetric-extension) tiles of every kernel
+    ((840, 48), 1),       # tall: several runs of the streaming level-1 kernels, interior periods, ragged last run
+    ((410, 300), 1),      # two column strips, last period of the run partly below the image
 ])
 def test_fused_vs_oracle_shapes(backend, shape, nlevels):
     rs = np.random.RandomState(shape[0] * 1000 + shape[1])
