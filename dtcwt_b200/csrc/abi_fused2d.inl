@@ -88,7 +88,8 @@ static int choose_periods(int rows, int ring, int64_t strips_times_n) {
 // level-1 forward: tile kernels (TMA-staged tile, packed row pass into shared memory, column pass from shared memory)
 constexpr uint32_t kMask19 = 0x7ffffu & ~(1u << 1) & ~(1u << 17);    // near_sym_b: taps 1 and m-2 are exactly zero
 constexpr uint32_t kMask13 = 0x1fffu & ~(1u << 1) & ~(1u << 11);
-typedef Fwd2d<SpecCol<13, kMask13>, SpecCol<19, kMask19>, 64, 64, 8> FwdT1_nsb;    // near_sym_b: exact-zero taps compiled out
+typedef Fwd2d<SpecCol<13, kMask13>, SpecCol<19, kMask19>, 64, 64, 8, BakedPhase<NearSymB_h0>, BakedPhase<NearSymB_h1s>,
+              BakedPhase<NearSymB_h1> > FwdT1_nsb;    // near_sym_b: exact-zero taps compiled out, column taps as immediates
 typedef Fwd2d<SpecCol<5>, SpecCol<7>, 64, 64, 8> FwdT1_5_7;                         // near_sym_a (+ legall 5/3)
 typedef Fwd2d<SpecCol<19>, SpecCol<19>, 64, 64, 8> FwdT1_19_19;                     // any odd pair up to 19 taps
 // level-1 forward: streaming kernels, selected with DTCWT_B200_FWD_STREAM=1 (h0 taps, h1 taps, masks of taps that may be non-zero, ring)
@@ -97,6 +98,8 @@ typedef FwdS1<19, 19, 0x7ffffu, 0x7ffffu, 20, 192, 2> FwdL1_19_19;          // a
 typedef FwdS1<5, 7, 0x1fu, 0x7fu, 8, 192, 3> FwdL1_5_7;                     // near_sym_a (+ legall 5/3)
 // level-1 inverse: streaming kernels (g0 taps, g1 taps, masks of taps that may be non-zero, ring, prefetch depth)
 typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1> > InvL1_nsb;   // near_sym_b, taps as immediates
+typedef InvS1<19, 13, kMask19, kMask13, 20, 2, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 3> InvL1_nsbB;   // experiment: 3 CTAs/SM
+typedef InvS1<19, 13, kMask19, kMask13, 24, 4, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 2> InvL1_nsbC;   // experiment: deeper prefetch
 typedef InvS1<19, 19, 0x7ffffu, 0x7ffffu, 24, 3> InvL1_19_19;       // any odd pair up to 19 taps (zero-padded)
 typedef InvS1<7, 5, 0x7fu, 0x1fu, 8, 2> InvL1_7_5;                  // near_sym_a (+ legall 3/5)
 // levels >= 2: q-shift pairs; every shipped family has a positive lowpass and a negative highpass tap correlation
@@ -277,6 +280,15 @@ int dtcwt_b200_inv2d_level1_f32(const float* z, const float* yh, float* out, int
         return launch_invs1<InvL1_7_5>(a, stream);
     }
     if (K1 == 13 && BakedTaps<NearSymB_g0>::same(a.g0) && BakedTaps<NearSymB_g1>::same(a.g1)) {
+        const int variant = env_int("DTCWT_B200_INV_VARIANT", 0);
+        if (variant == 1) {
+            a.periods = choose_periods(a.rows, InvL1_nsbB::RING, (int64_t)InvL1_nsbB::tiles_c(a) * a.n);
+            return launch_invs1<InvL1_nsbB>(a, stream);
+        }
+        if (variant == 2) {
+            a.periods = choose_periods(a.rows, InvL1_nsbC::RING, (int64_t)InvL1_nsbC::tiles_c(a) * a.n);
+            return launch_invs1<InvL1_nsbC>(a, stream);
+        }
         a.periods = choose_periods(a.rows, InvL1_nsb::RING, (int64_t)InvL1_nsb::tiles_c(a) * a.n);
         return launch_invs1<InvL1_nsb>(a, stream);
     }

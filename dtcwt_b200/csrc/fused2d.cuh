@@ -29,6 +29,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "baked_taps.h"
 
 namespace dtcwt {
 
@@ -153,9 +154,18 @@ DTCWT_D void fir_gather(const float (&w)[WN], const PhaseTaps& t, float (&acc)[F
     }
 }
 
+// Tap source of a scatter: the kernel arguments, or a table baked into the instance (FFMA2 immediates).
+struct RtPhase {
+    static DTCWT_D float get(const PhaseTaps& t, int ph, int k) { return t.t[ph][k]; }
+};
+template <class B>
+struct BakedPhase {
+    static DTCWT_D float get(const PhaseTaps&, int, int k) { return B::get(k); }
+};
+
 // Input row j (relative to the window start, HALO rows before the first group) contributes to
 // the outputs whose support contains it; j is a compile-time constant after unrolling.
-template <class F, int NG, int HALO>
+template <class F, int NG, int HALO, class TS = RtPhase>
 DTCWT_D void fir_scatter(const int j, const F2 v, const PhaseTaps& t, F2 (&acc)[F::P * NG]) {
 #pragma unroll
     for (int ii = 0; ii < NG; ++ii) {
@@ -163,7 +173,7 @@ DTCWT_D void fir_scatter(const int j, const F2 v, const PhaseTaps& t, F2 (&acc)[
         for (int ph = 0; ph < F::P; ++ph) {
             const int num = j - HALO - F::Q * ii - F::b(ph);
             if (num >= 0 && (num % F::S) == 0 && (num / F::S) < F::K && F::on(ph, num / F::S)) {
-                acc[F::P * ii + ph] = fma2(t.t[ph][num / F::S], v, acc[F::P * ii + ph]);
+                acc[F::P * ii + ph] = fma2(TS::get(t, ph, num / F::S), v, acc[F::P * ii + ph]);
             }
         }
     }
@@ -194,7 +204,7 @@ struct Fwd2dArgs {
     PairTab ph0, ph1s;              // level 1 only: the row-pass taps as pairs (t[k], t[k-1]) for the packed row pass
 };
 
-template <class H0, class H1, int GH_, int GW_, int NGV_>
+template <class H0, class H1, int GH_, int GW_, int NGV_, class TV0 = RtPhase, class TV1S = RtPhase, class TV1 = RtPhase>
 struct Fwd2d {
     typedef Fwd2dArgs Args;
     static constexpr int P = H0::P, Q = H0::Q;
@@ -213,7 +223,7 @@ struct Fwd2d {
     static constexpr int kSmemFloats = RX * CX + 2 * RX * CA;
     static constexpr int kThreads = kFusedThreads;
     static constexpr int kPhases = 5;
-    static constexpr int kMinBlocks = 2;
+    static constexpr int kMinBlocks = (kSmemFloats * 4 * 3 <= 220 * 1024) ? 3 : 2;      // CTAs per SM the shared memory allows
     static_assert(P == H1::P && Q == H1::Q, "filter pair must share its rate");
     static_assert((NOUT % 2) == 0 && (GH % NGV) == 0 && (GW % NGH) == 0 && (CA % 2) == 0, "tile shape");
     static_assert(P * NGH == 4 || P * NGH == 2, "row task writes a float4 or float2");
@@ -337,20 +347,18 @@ struct Fwd2d {
         }
     }
 
-    // q2c of NOUT rows x 2 columns (transform2d.py:301-322; the 1/sqrt2 is already in the taps)
-    static DTCWT_D void store_q2c(const Args& a, const F2 (&y)[NOUT], int bz, int gi0, int gj, int band0, int band1) {
-        if (gj >= a.out_cols / 2) return;
-        float* z = a.yh + 2 * ((int64_t)bz * a.zs_n + gj);
+    // q2c of NOUT rows x 2 columns (transform2d.py:301-322; the 1/sqrt2 is already in the taps): z0 / z1 point at the
+    // first quad row of the two sub-bands, rs = floats per quad row, nq = quad rows that lie inside the image
+    static DTCWT_D void store_q2c(const F2 (&y)[NOUT], float* z0, float* z1, int64_t rs, int nq) {
 #pragma unroll
         for (int q = 0; q < NOUT / 2; ++q) {
-            const int gi = gi0 + q;
-            if (gi < a.out_rows / 2) {
+            if (q < nq) {
                 const float A = y[2 * q].x, B = y[2 * q].y, C = y[2 * q + 1].x, D = y[2 * q + 1].y;
-                F2 z0, z1;
-                z0.x = A - D; z0.y = B + C;
-                z1.x = A + D; z1.y = B - C;
-                *reinterpret_cast<F2*>(z + 2 * (band0 * a.zs_band + gi * a.zs_row)) = z0;
-                *reinterpret_cast<F2*>(z + 2 * (band1 * a.zs_band + gi * a.zs_row)) = z1;
+                F2 w0, w1;
+                w0.x = A - D; w0.y = B + C;
+                w1.x = A + D; w1.y = B - C;
+                *reinterpret_cast<F2*>(z0 + q * rs) = w0;
+                *reinterpret_cast<F2*>(z1 + q * rs) = w1;
             }
         }
     }
@@ -370,26 +378,31 @@ struct Fwd2d {
 #pragma unroll
             for (int j = 0; j < NR; ++j) {
                 const F2 v = *reinterpret_cast<const F2*>(As + (lrow + j) * CA + 2 * cp);
-                fir_scatter<H0, NGV, HL>(j, v, a.v0, lo);
-                fir_scatter<H1, NGV, HL>(j, v, a.v1s, hi);
+                fir_scatter<H0, NGV, HL, TV0>(j, v, a.v0, lo);
+                fir_scatter<H1, NGV, HL, TV1S>(j, v, a.v1s, hi);
             }
-            if (ocol < a.out_cols) {
+            // output rows / quad rows of this task that lie inside the image (none when its columns lie outside)
+            const int nrow = (ocol < a.out_cols) ? a.out_rows - orow : 0;
+            const int nq = nrow / 2;                              // out_rows is even
+            float* zb = a.yh + 2 * ((int64_t)bz * a.zs_n + (int64_t)(orow / 2) * a.zs_row + ocol / 2);
+            const int64_t bs = 2 * a.zs_band, rs = 2 * a.zs_row;
+            {
                 float* dst = a.lolo + ((int64_t)bz * a.out_rows + orow) * a.out_cols + ocol;
 #pragma unroll
                 for (int i = 0; i < NOUT; ++i)
-                    if (orow + i < a.out_rows) *reinterpret_cast<F2*>(dst + (int64_t)i * a.out_cols) = lo[i];
+                    if (i < nrow) *reinterpret_cast<F2*>(dst + (int64_t)i * a.out_cols) = lo[i];
             }
-            store_q2c(a, hi, bz, orow / 2, ocol / 2, 0, 5);      // vertical high x horizontal low
+            store_q2c(hi, zb, zb + 5 * bs, rs, nq);              // vertical high x horizontal low -> bands 0, 5
 #pragma unroll
             for (int i = 0; i < NOUT; ++i) { lo[i].x = lo[i].y = 0.f; hi[i].x = hi[i].y = 0.f; }
 #pragma unroll
             for (int j = 0; j < NR; ++j) {
                 const F2 v = *reinterpret_cast<const F2*>(Bs + (lrow + j) * CA + 2 * cp);
-                fir_scatter<H0, NGV, HL>(j, v, a.v0, lo);
-                fir_scatter<H1, NGV, HL>(j, v, a.v1, hi);
+                fir_scatter<H0, NGV, HL, TV0>(j, v, a.v0, lo);
+                fir_scatter<H1, NGV, HL, TV1>(j, v, a.v1, hi);
             }
-            store_q2c(a, lo, bz, orow / 2, ocol / 2, 2, 3);      // vertical low x horizontal high
-            store_q2c(a, hi, bz, orow / 2, ocol / 2, 1, 4);      // high x high
+            store_q2c(lo, zb + 2 * bs, zb + 3 * bs, rs, nq);     // vertical low x horizontal high -> bands 2, 3
+            store_q2c(hi, zb + 1 * bs, zb + 4 * bs, rs, nq);     // high x high -> bands 1, 4
         }
     }
 

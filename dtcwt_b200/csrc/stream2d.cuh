@@ -30,7 +30,6 @@
 #include <type_traits>
 
 #include "fused2d.cuh"
-#include "baked_taps.h"
 
 namespace dtcwt {
 
@@ -84,7 +83,7 @@ struct InvS1Args {
     PairTab p0, p1;                 // row pass (tap pairs)
 };
 
-template <int K0, int K1, uint32_t M0, uint32_t M1, int RING_, int NST_, class T0 = ArgTaps, class T1 = ArgTaps>
+template <int K0, int K1, uint32_t M0, uint32_t M1, int RING_, int NST_, class T0 = ArgTaps, class T1 = ArgTaps, int MINB_ = 2>
 struct InvS1 {
     typedef InvS1Args Args;
     static constexpr int RING = RING_, PER = RING_ / 2, NST = NST_;
@@ -98,7 +97,7 @@ struct InvS1 {
     static constexpr int WS0 = (CQ - C0) / 4 * 4, WE0 = round_up(CQ + 8 + C0, 4);   // y1 window of a row task
     static constexpr int WS1 = (CQ - C1) / 4 * 4, WE1 = round_up(CQ + 8 + C1, 4);   // y2 window
     static constexpr int kSmemFloats = 2 * RING * CYP;
-    static constexpr int kMinBlocks = 2;
+    static constexpr int kMinBlocks = MINB_;
     static_assert(K0 >= K1 && (K0 & 1) && (K1 & 1) && K0 <= kStreamMaxTaps && (M0 & 1u), "filter pair");
     static_assert(RING >= CQ + C0 + 1 && (RING % 2) == 0 && (PER % NST) == 0, "ring");
     static_assert(8 * (NSEG - 1) + WE0 <= CY && 8 * (NSEG - 1) + WE1 <= CY, "row-pass window inside the smem row");
