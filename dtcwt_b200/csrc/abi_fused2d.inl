@@ -103,7 +103,7 @@ typedef InvS1<19, 13, kMask19, kMask13, 24, 4, BakedTaps<NearSymB_g0>, BakedTaps
 typedef InvS1<19, 19, 0x7ffffu, 0x7ffffu, 24, 3> InvL1_19_19;       // any odd pair up to 19 taps (zero-padded)
 typedef InvS1<7, 5, 0x7fu, 0x1fu, 8, 2> InvL1_7_5;                  // near_sym_a (+ legall 3/5)
 // levels >= 2: q-shift pairs; every shipped family has a positive lowpass and a negative highpass tap correlation
-template <int M> struct FwdLq { typedef Fwd2d<SpecDec<M, true>, SpecDec<M, false>, 32, 16, 2> type; };
+template <int M> struct FwdLq { typedef Fwd2d<SpecDec<M, true>, SpecDec<M, false>, 32, 16, 4> type; };
 template <int M> struct InvLq { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4> type; };
 
 static int fwd_common(Fwd2dArgs& a, const float* x, float* lolo, float* yh, int64_t n, int64_t rows, int64_t cols,
@@ -228,6 +228,12 @@ int dtcwt_b200_fwd2d_levelq_f32(const float* x, float* lolo, float* yh, int64_t 
     taps_dec(a.v0, lo_a, lo_b, m, true, 1.0);
     taps_dec(a.v1, hi_a, hi_b, m, false, 1.0);
     taps_dec(a.v1s, hi_a, hi_b, m, false, kInvSqrt2);
+    for (int k = 0; k <= kStreamMaxTaps; ++k) {          // row pass: (lowpass phase ph, highpass phase 1 - ph) tap pairs
+        a.ph0.p[k].x = (k < m) ? a.h0.t[0][k] : 0.f;
+        a.ph0.p[k].y = (k < m) ? a.h1s.t[1][k] : 0.f;
+        a.ph1s.p[k].x = (k < m) ? a.h0.t[1][k] : 0.f;
+        a.ph1s.p[k].y = (k < m) ? a.h1s.t[0][k] : 0.f;
+    }
     if (m == 10) return launch_fwd2d<FwdLq<10>::type>(a, stream);
     if (m == 14) return launch_fwd2d<FwdLq<14>::type>(a, stream);
     return launch_fwd2d<FwdLq<18>::type>(a, stream);

@@ -214,8 +214,10 @@ struct Fwd2d {
     static constexpr int HR = cmax(spec_hi<H0>(), spec_hi<H1>());
     static constexpr int HLA = round_up(HL, 4), HRA = round_up(HR, 4);
     static constexpr int RX = Q * GH + HL + HR;             // input tile rows
-    static constexpr int CX = Q * GW + HLA + HRA;           // input tile columns (multiple of 4)
-    static constexpr int CA = P * GW;                       // columns of the row-pass outputs
+    // input tile pitch (multiple of 4) and pitch of the row-pass outputs; the q-shift row pass reads 32-byte segments
+    // with adjacent lanes on adjacent rows, which is free of bank conflicts when the pitch is 4 (mod 8) floats
+    static constexpr int CX = Q * GW + HLA + HRA + ((P == 2 && (Q * GW + HLA + HRA) % 8 == 0) ? 4 : 0);
+    static constexpr int CA = P * GW + ((P == 2) ? 4 : 0);
     static constexpr int WN = 4 + HLA + HRA;                // register window of a row task
     static constexpr int NSEG = GW / NGH;
     static constexpr int NR = Q * NGV + HL + HR;            // input rows of a column task
@@ -223,6 +225,9 @@ struct Fwd2d {
     static constexpr int kSmemFloats = RX * CX + 2 * RX * CA;
     static constexpr int kThreads = kFusedThreads;
     static constexpr int kPhases = 5;
+    // q-shift levels: one resident wave of CTAs walks over the tiles and prefetches the next tile during the column
+    // pass (measured 4 % faster); level 1 is faster with one CTA per tile (profiles/r1_03)
+    static constexpr bool kPersistent = (P != 1);
     static constexpr int kMinBlocks = (kSmemFloats * 4 * 3 <= 220 * 1024) ? 3 : 2;      // CTAs per SM the shared memory allows
     static_assert(P == H1::P && Q == H1::Q, "filter pair must share its rate");
     static_assert((NOUT % 2) == 0 && (GH % NGV) == 0 && (GW % NGH) == 0 && (CA % 2) == 0, "tile shape");
@@ -306,10 +311,60 @@ struct Fwd2d {
     template <class HH = H0>
     static DTCWT_D typename std::enable_if<!(HH::P == 1 && HH::Q == 1)>::type phase_rows_packed(const Args&, float*, int) {}
 
+    // q-shift levels (P = 2, Q = 4): lowpass phase 0 and highpass phase 1 read the same samples (phases 1 and 0 the
+    // neighbouring ones), so one FFMA2 of a scalar sample with the tap pair (h0[ph][k], h1[1-ph][k]) advances both
+    // filters (pairs prepared by the host in ph0 / ph1s).  One task = one tile row x NGD groups (4 * NGD input columns).
+    static constexpr int NGD = 2;
+    template <class HH = H0>
+    static DTCWT_D typename std::enable_if<HH::P == 2 && HH::Q == 4>::type phase_rows_dec(const Args& a, float* sm, int tid) {
+        constexpr int M = H0::K;
+        constexpr int OFF = HLA - (M - 2);                                  // window index of the first even-phase sample
+        constexpr int WND = round_up(4 * (NGD - 1) + OFF + 2 * (M - 1) + 2, 4);
+        constexpr int NSD = GW / NGD;
+        static_assert(H0::b(0) == -M + 2 && H1::b(1) == -M + 2 && H0::b(1) == -M + 3 && H1::b(0) == -M + 3, "phase pairing");
+        static_assert((GW % NGD) == 0 && (RX % 2) == 0 && 4 * NGD * (NSD - 1) + WND <= CX && NGD == 2, "q-shift row task");
+        const float* Xs = sm;
+        float* As = sm + RX * CX;
+        float* Bs = As + RX * CA;
+        for (int task = tid; task < RX * NSD; task += kThreads) {
+            const int half = task >> 1;
+            const int lr = 2 * (half / NSD) + (task & 1), seg = half % NSD;
+            F2 m1[NGD], m2[NGD];                                            // (A[2g], B[2g+1]) and (A[2g+1], B[2g])
+#pragma unroll
+            for (int g = 0; g < NGD; ++g) { m1[g] = zero2(); m2[g] = zero2(); }
+            const F4* src = reinterpret_cast<const F4*>(Xs + lr * CX + 4 * NGD * seg);
+#pragma unroll
+            for (int c = 0; c < WND / 4; ++c) {
+                const F4 v = src[c];
+                const float w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                    for (int g = 0; g < NGD; ++g) {
+                        const int num = 4 * c + i - 4 * g - OFF;
+                        if (num >= 0 && (num & 1) == 0 && num / 2 < M) m1[g] = fma2(w[i], a.ph0.p[num / 2], m1[g]);
+                        if (num >= 1 && (num & 1) == 1 && (num - 1) / 2 < M) m2[g] = fma2(w[i], a.ph1s.p[(num - 1) / 2], m2[g]);
+                    }
+                }
+            }
+            F4 va, vb;
+            va.x = m1[0].x; va.y = m2[0].x; va.z = m1[1].x; va.w = m2[1].x;
+            vb.x = m2[0].y; vb.y = m1[0].y; vb.z = m2[1].y; vb.w = m1[1].y;
+            *reinterpret_cast<F4*>(As + lr * CA + 2 * NGD * seg) = va;
+            *reinterpret_cast<F4*>(Bs + lr * CA + 2 * NGD * seg) = vb;
+        }
+    }
+    template <class HH = H0>
+    static DTCWT_D typename std::enable_if<!(HH::P == 2 && HH::Q == 4)>::type phase_rows_dec(const Args&, float*, int) {}
+
     // phase 3: row pass, one task = one tile row x 4 input columns
     static DTCWT_D void phase_rows(const Args& a, float* sm, int bx, int by, int bz, int tid) {
         if (P == 1 && Q == 1) {
             phase_rows_packed(a, sm, tid);
+            return;
+        }
+        if (P == 2 && Q == 4) {
+            phase_rows_dec(a, sm, tid);
             return;
         }
         const float* Xs = sm;
@@ -367,8 +422,9 @@ struct Fwd2d {
     static DTCWT_D void phase_cols(const Args& a, float* sm, int bx, int by, int bz, int tid) {
         const float* As = sm + RX * CX;
         const float* Bs = As + RX * CA;
-        for (int task = tid; task < (CA / 2) * (GH / NGV); task += kThreads) {
-            const int strip = task / (CA / 2), cp = task - strip * (CA / 2);
+        constexpr int NCP = P * GW / 2;                           // column pairs of the tile (CA may be padded)
+        for (int task = tid; task < NCP * (GH / NGV); task += kThreads) {
+            const int strip = task / NCP, cp = task - strip * NCP;
             const int lrow = Q * NGV * strip;
             const int orow = P * (GH * by + NGV * strip);        // first output row (LoLo coordinates)
             const int ocol = P * GW * bx + 2 * cp;

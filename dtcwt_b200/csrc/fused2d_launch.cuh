@@ -42,6 +42,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
         : "memory");
 }
 
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();      // a lost transaction must not hang the GPU
+    }
+}
+
 template <class K, int PH, bool DONE = (PH >= K::kPhases)>
 struct PhaseRunner {
     static __device__ __forceinline__ void run(const typename K::Args& a, float* sm, int bx, int by, int bz, int tid) {
@@ -57,27 +65,54 @@ struct PhaseRunner<K, PH, true> {
 
 extern __shared__ __align__(128) float fused_smem[];
 
+// Persistent forward tile kernel: a CTA walks over tiles blockIdx.x, blockIdx.x + gridDim.x, ... (column index fastest,
+// so CTAs running side by side work on neighbouring tiles).  The input tile is only needed until the row pass has
+// turned it into A / B, so the TMA load of the NEXT tile is issued right after the row pass and lands in the same
+// buffer while the column pass -- 60 % of the arithmetic -- runs.
 template <class K>
 __global__ void __launch_bounds__(kFusedThreads, K::kMinBlocks)
 fwd2d_kernel(const __grid_constant__ typename K::Args a, const __grid_constant__ CUtensorMap tmap) {
     __shared__ __align__(8) uint64_t bar;
-    const int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z, tid = threadIdx.x;
+    const int tid = threadIdx.x;
+    const int tc = K::tiles_c(a), tr = K::tiles_r(a);
+    const int ntiles = tc * tr * a.n;
     if (a.use_tma) {
         if (tid == 0) {
             mbar_init(&bar, 1);
             fence_mbar_init();
         }
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0 && (int)blockIdx.x < ntiles) {
+            const int t = blockIdx.x, bx = t % tc, by = (t / tc) % tr, bz = t / (tc * tr);
             mbar_expect_tx(&bar, (uint32_t)(K::RX * K::CX * sizeof(float)));
             tma_load_3d(fused_smem, &tmap, K::col0(bx) - a.pc_lo, K::row0(by) - a.pr_lo, bz, &bar);
         }
-        uint32_t spins = 0;
-        while (!mbar_try_wait(&bar, 0)) {
-            if (++spins > (1u << 26)) __trap();      // a lost transaction must not hang the GPU
-        }
     }
-    PhaseRunner<K, 0>::run(a, fused_smem, bx, by, bz, tid);
+    uint32_t parity = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int bx = t % tc, by = (t / tc) % tr, bz = t / (tc * tr);
+        if (a.use_tma) {
+            mbar_wait(&bar, parity);
+            parity ^= 1u;
+        } else {
+            K::template phase<0>(a, fused_smem, bx, by, bz, tid);
+        }
+        __syncthreads();
+        K::template phase<1>(a, fused_smem, bx, by, bz, tid);
+        __syncthreads();
+        K::template phase<2>(a, fused_smem, bx, by, bz, tid);
+        __syncthreads();
+        K::template phase<3>(a, fused_smem, bx, by, bz, tid);
+        if (a.use_tma) fence_proxy_async_smem();      // this thread's reads / patch writes of the tile precede the next TMA fill
+        __syncthreads();
+        if (a.use_tma && tid == 0 && t + (int)gridDim.x < ntiles) {
+            const int n = t + gridDim.x, nx = n % tc, ny = (n / tc) % tr, nz = n / (tc * tr);
+            mbar_expect_tx(&bar, (uint32_t)(K::RX * K::CX * sizeof(float)));
+            tma_load_3d(fused_smem, &tmap, K::col0(nx) - a.pc_lo, K::row0(ny) - a.pr_lo, nz, &bar);
+        }
+        K::template phase<4>(a, fused_smem, bx, by, bz, tid);
+        __syncthreads();
+    }
 }
 
 template <class K>
@@ -99,14 +134,6 @@ __global__ void __launch_bounds__(kStreamThreads, K::kMinBlocks) invs1_kernel(co
             K::rows(a, fused_smem, bx, by, bz, tid, p);
             __syncthreads();
         }
-    }
-}
-
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();      // a lost transaction must not hang the GPU
     }
 }
 
@@ -208,8 +235,16 @@ static int launch_fwd2d(typename K::Args& a, void* stream) {
         if (r == CUDA_SUCCESS) a.use_tma = 1;
     }
     if (a.n == 0) return DTCWT_B200_OK;
-    const dim3 grid((unsigned)K::tiles_c(a), (unsigned)K::tiles_r(a), (unsigned)a.n);
-    fwd2d_kernel<K><<<grid, kFusedThreads, smem, (cudaStream_t)stream>>>(a, map);
+    const int64_t ntiles = (int64_t)K::tiles_c(a) * K::tiles_r(a) * a.n;
+    if (ntiles > 0x7fffffffLL) return DTCWT_B200_EUNSUPPORTED;
+    int dev = 0, sms = 0, per_sm = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fwd2d_kernel<K>, kFusedThreads, smem)) != cudaSuccess)
+        return (int)e;
+    int64_t ctas = (int64_t)sms * (per_sm > 0 ? per_sm : 1);          // one wave of resident CTAs, each walks over tiles
+    if (ctas > ntiles || !K::kPersistent) ctas = ntiles;
+    fwd2d_kernel<K><<<(unsigned)ctas, kFusedThreads, smem, (cudaStream_t)stream>>>(a, map);
     return (int)cudaGetLastError();
 }
 

@@ -43,12 +43,14 @@ struct EmuPhases<K, PH, true> {
     static void run(const typename K::Args&, float*, int, int, int) {}
 };
 
+// Tiles run in DESCENDING order: a tile that writes outside its own outputs (a GPU race between CTAs) then
+// clobbers results of tiles that already ran instead of being silently overwritten by them.
 template <class K>
 static int emu_launch(typename K::Args& a) {
     std::vector<float> sm(K::kSmemFloats);
-    for (int bz = 0; bz < a.n; ++bz)
-        for (int by = 0; by < K::tiles_r(a); ++by)
-            for (int bx = 0; bx < K::tiles_c(a); ++bx) {
+    for (int bz = a.n - 1; bz >= 0; --bz)
+        for (int by = K::tiles_r(a) - 1; by >= 0; --by)
+            for (int bx = K::tiles_c(a) - 1; bx >= 0; --bx) {
                 for (size_t i = 0; i < sm.size(); ++i) sm[i] = NAN;
                 EmuPhases<K, 0>::run(a, sm.data(), bx, by, bz);
             }
