@@ -33,11 +33,25 @@ SIDE = 4096
 NLEVELS = 4
 BIORT, QSHIFT = "near_sym_b", "qshift_b"
 ALGO_BYTES_PER_PIXEL = 40.0     # fwd: read 4 + write 16; inv: read 16 + write 4
-# algorithmic bytes per INPUT pixel of each fused kernel (DESIGN.md "kernels")
+# algorithmic bytes per level-1 pixel and STEP of each fused entry point (DESIGN.md "kernels"); the q-shift entry
+# points are launched once per level 2..4 (8 + 2 + 0.5 B/pixel), so their per-launch figure is the per-step one
+# divided by the launches per step
 KERNEL_ALGO_BYTES = {
     "dtcwt_b200_fwd2d_level1_f32": 20.0,   # read X 4, write LoLo 4 + Yh 12
     "dtcwt_b200_inv2d_level1_f32": 20.0,   # read LoLo 4 + Yh 12, write Z 4
+    "dtcwt_b200_fwd2d_levelq_f32": 10.5,   # levels 2..4: read 4 + write LoLo 1 + Yh 3 per input pixel of the level
+    "dtcwt_b200_inv2d_levelq_f32": 10.5,
 }
+
+
+def measured_traffic(sym, pixels):
+    """dram__bytes_read + dram__bytes_write of one launch from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, bytes per level-1 pixel), scaled to this run's launch; None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return round(json.load(f)[sym]["dram_bytes_per_pixel"] * pixels / 1e9, 4)
+    except Exception:
+        return None
 
 
 def parse():
@@ -163,14 +177,35 @@ def workload_config(args, side=None, images=None):
 
 # =============================================================================== clocks sampler
 class ClockSampler(object):
+    """SM clock, power and throttle reasons DURING the timed region: NVML polled every few ms from a thread
+    (nvidia-smi takes longer to start than a 10-step timed region lasts); nvidia-smi -lms as the fallback."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.stop_flag = index, [], None, None, False
+        self.sm, self.power, self.reasons, self.max_mhz = [], [], set(), None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.index
+            if visible:
+                ids = [v.strip() for v in visible.split(",") if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    phys = int(ids[self.index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
@@ -181,11 +216,35 @@ class ClockSampler(object):
         self.thread = threading.Thread(target=self._pump, daemon=True)
         self.thread.start()
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.power.append(n.nvmlDeviceGetPowerUsage(self.handle) / 1e3)
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for name, bit in self.BITS:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                    "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(sm),
+                    "power_w_max": max(self.power) if self.power else None, "source": "nvml, 4 ms polling inside the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -208,10 +267,9 @@ class ClockSampler(object):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
-        # "under load": the upper half of the samples (the sampler also sees idle gaps)
         med = sm[len(sm) // 2] if sm else None
         return {"sm_mhz": med, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power) if power else None}
+                "samples": len(sm), "power_w_max": max(power) if power else None, "source": "nvidia-smi -lms 100"}
 
 
 # =============================================================================== GPU legs
@@ -257,7 +315,7 @@ def run_ours(args):
     import dtcwt_b200
     from dtcwt_b200 import _lib, coeffs, parallel
 
-    steps = args.steps if args.steps is not None else 10
+    steps = args.steps if args.steps is not None else 30
     warm = args.warmup if args.warmup is not None else 3
     if warm < 3:
         warm = 3                                   # timing rule: at least 3 warm-up steps
@@ -356,9 +414,14 @@ def run_ours(args):
         sym, (tot_ms, n) = top
         avg_ms = tot_ms / n
         share = tot_ms / ms_total
+        traffic = None
         if sym in KERNEL_ALGO_BYTES:
-            algo = KERNEL_ALGO_BYTES[sym] * nimg * side * side
-            note = "%s: %.0f B/input pixel algorithmic" % (sym, KERNEL_ALGO_BYTES[sym])
+            per_step = n / steps
+            algo = KERNEL_ALGO_BYTES[sym] * nimg * side * side / per_step
+            note = "%s: %.1f B/pixel algorithmic per step, %d launch(es) per step; traffic = GB per launch from the " \
+                   "committed ncu capture (profiles/ncu_traffic.json)" % (sym, KERNEL_ALGO_BYTES[sym], per_step)
+            if per_step == 1:
+                traffic = measured_traffic(sym, nimg * side * side)
         else:
             # generic (unfused) path: no single kernel dominates by design; report the whole step
             algo, avg_ms, sym = ALGO_BYTES_PER_PIXEL * nimg * side * side, ms_total / steps, "whole step (unfused generic kernels)"
@@ -366,9 +429,10 @@ def run_ours(args):
             share = 1.0
         ach = algo / (avg_ms / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": sym, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src, "note": note,
+                    "frac": round(ach / peak, 4), "traffic": traffic, "traffic_unit": "GB per launch",
+                    "algorithmic_gb_per_launch": round(algo / 1e9, 4), "peak_source": peak_src, "note": note,
                     "avg_launch_ms": round(avg_ms, 4), "share_of_step": round(share, 4),
-                    "whole_step_frac": round(ALGO_BYTES_PER_PIXEL * nimg * side * side * steps / (ms_total / 1e3) / 1e9 / peak, 4),
+                    "whole_step_frac": round(ALGO_BYTES_PER_PIXEL * nimg * side * side * steps / (ms_total / 1e3) / 1e9 / peak, 4),   # per GPU
                     "kernels_ms_per_step": {k: round(v[0] / steps, 4) for k, v in sorted(per.items())}}
     _lib.set_launch_hook(None)
 
@@ -383,7 +447,7 @@ def run_ours(args):
             "ms_per_step": round(ms_total / steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
-            "hbm_frac_of_measured_peak": round(ALGO_BYTES_PER_PIXEL * value * 1e6 / 1e9 / peak, 4),
+            "hbm_frac_of_measured_peak": round(ALGO_BYTES_PER_PIXEL * value * 1e6 / 1e9 / (peak * world), 4),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

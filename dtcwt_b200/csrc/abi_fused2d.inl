@@ -98,8 +98,8 @@ typedef FwdS1<19, 19, 0x7ffffu, 0x7ffffu, 20, 192, 2> FwdL1_19_19;          // a
 typedef FwdS1<5, 7, 0x1fu, 0x7fu, 8, 192, 3> FwdL1_5_7;                     // near_sym_a (+ legall 5/3)
 // level-1 inverse: streaming kernels (g0 taps, g1 taps, masks of taps that may be non-zero, ring, prefetch depth)
 typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1> > InvL1_nsb;   // near_sym_b, taps as immediates
-typedef InvS1<19, 13, kMask19, kMask13, 20, 2, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 3> InvL1_nsbB;   // experiment: 3 CTAs/SM
-typedef InvS1<19, 13, kMask19, kMask13, 24, 4, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 2> InvL1_nsbC;   // experiment: deeper prefetch
+typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 2, 1> InvL1_nsbB;   // diagnosis: memory only
+typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 2, 2> InvL1_nsbC;   // diagnosis: arithmetic only
 typedef InvS1<19, 19, 0x7ffffu, 0x7ffffu, 24, 3> InvL1_19_19;       // any odd pair up to 19 taps (zero-padded)
 typedef InvS1<7, 5, 0x7fu, 0x1fu, 8, 2> InvL1_7_5;                  // near_sym_a (+ legall 3/5)
 // levels >= 2: q-shift pairs; every shipped family has a positive lowpass and a negative highpass tap correlation

@@ -83,7 +83,8 @@ struct InvS1Args {
     PairTab p0, p1;                 // row pass (tap pairs)
 };
 
-template <int K0, int K1, uint32_t M0, uint32_t M1, int RING_, int NST_, class T0 = ArgTaps, class T1 = ArgTaps, int MINB_ = 2>
+// DBG (diagnosis builds only, results are wrong): 1 = memory traffic without the arithmetic, 2 = arithmetic without the loads
+template <int K0, int K1, uint32_t M0, uint32_t M1, int RING_, int NST_, class T0 = ArgTaps, class T1 = ArgTaps, int MINB_ = 2, int DBG = 0>
 struct InvS1 {
     typedef InvS1Args Args;
     static constexpr int RING = RING_, PER = RING_ / 2, NST = NST_;
@@ -132,6 +133,11 @@ struct InvS1 {
         if (EDGE) {
             bool f;
             q = fold_quad(q, a.rows / 2, f);
+        }
+        if (DBG == 2) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { r.v[i].x = (float)q; r.v[i].y = (float)(q + i); }
+            return;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) r.v[i] = *reinterpret_cast<const F2*>(th.ptr[i] + (int64_t)q * th.stride[i]);   // one IMAD.WIDE
@@ -199,14 +205,21 @@ struct InvS1 {
                 flip_quad(fr, th.fc != 0, at, ab);
                 flip_quad(fr, th.fc != 0, bt, bb);
             }
-            ring_scatter<T0, K0, M0, C0, true, RING>(2 * u, at, a.g0, th.acc);
-            ring_scatter<T1, K1, M1, C1, false, RING>(2 * u, bt, a.g1, th.acc);
+            if (DBG == 1) {
+                th.acc[pmod(2 * u - CQ, RING)].x = at.x + bt.y; th.acc[pmod(2 * u - CQ, RING)].y = at.y + bt.x;
+                th.acc[pmod(2 * u + 1 - CQ, RING)].x = ab.x + bb.y; th.acc[pmod(2 * u + 1 - CQ, RING)].y = ab.y + bb.x;
+            } else {
+                ring_scatter<T0, K0, M0, C0, true, RING>(2 * u, at, a.g0, th.acc);
+                ring_scatter<T1, K1, M1, C1, false, RING>(2 * u, bt, a.g1, th.acc);
+            }
             if (emit) {                // rows 2u and 2u+1 of this period's block are complete
                 *reinterpret_cast<F2*>(y + (2 * u) * CYP) = th.acc[pmod(2 * u - CQ, RING)];
                 *reinterpret_cast<F2*>(y + (2 * u + 1) * CYP) = th.acc[pmod(2 * u + 1 - CQ, RING)];
             }
-            ring_scatter<T0, K0, M0, C0, true, RING>(2 * u + 1, ab, a.g0, th.acc);
-            ring_scatter<T1, K1, M1, C1, false, RING>(2 * u + 1, bb, a.g1, th.acc);
+            if (DBG != 1) {
+                ring_scatter<T0, K0, M0, C0, true, RING>(2 * u + 1, ab, a.g0, th.acc);
+                ring_scatter<T1, K1, M1, C1, false, RING>(2 * u + 1, bb, a.g1, th.acc);
+            }
         }
     }
 
@@ -242,13 +255,19 @@ struct InvS1 {
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[i] = zero2();
             const F4* s1 = reinterpret_cast<const F4*>(y1 + yr * CYP + 8 * seg + WS0);
-#pragma unroll
-            for (int c = 0; c < (WE0 - WS0) / 4; ++c)
-                pair_gather4<K0, M0, C0, WS0 - CQ, 8, WE0 - WS0>(4 * c, s1[c], a.p0, acc);
             const F4* s2 = reinterpret_cast<const F4*>(y2 + yr * CYP + 8 * seg + WS1);
+            if (DBG == 1) {
+                const F4 p = s1[1], q = s1[2], r = s2[1], t = s2[2];
+                acc[0].x = p.x + r.x; acc[0].y = p.y + r.y; acc[1].x = p.z + r.z; acc[1].y = p.w + r.w;
+                acc[2].x = q.x + t.x; acc[2].y = q.y + t.y; acc[3].x = q.z + t.z; acc[3].y = q.w + t.w;
+            } else {
 #pragma unroll
-            for (int c = 0; c < (WE1 - WS1) / 4; ++c)
-                pair_gather4<K1, M1, C1, WS1 - CQ, 8, WE1 - WS1>(4 * c, s2[c], a.p1, acc);
+                for (int c = 0; c < (WE0 - WS0) / 4; ++c)
+                    pair_gather4<K0, M0, C0, WS0 - CQ, 8, WE0 - WS0>(4 * c, s1[c], a.p0, acc);
+#pragma unroll
+                for (int c = 0; c < (WE1 - WS1) / 4; ++c)
+                    pair_gather4<K1, M1, C1, WS1 - CQ, 8, WE1 - WS1>(4 * c, s2[c], a.p1, acc);
+            }
             float* d = img + (int64_t)r * a.cols + c0;
             if (a.out_vec4 && c0 + 8 <= a.cols) {
                 F4 v;

@@ -82,6 +82,26 @@ def test_fused_vs_oracle_shapes(backend, shape, nlevels):
     check_roundtrip(X, "near_sym_b", "qshift_b", nlevels, gain)
 
 
+@pytest.mark.parametrize("shape", [(64, 64), (840, 200), (410, 300), (65, 131)])
+def test_streaming_forward_level1(backend, monkeypatch, shape):
+    """The streaming level-1 forward kernel (stream2d.cuh FwdS1; the default forward is the tile kernel, which measured
+    faster) is kept selectable with DTCWT_B200_FWD_STREAM=1 and must give the same pyramid."""
+    rs = np.random.RandomState(shape[0] + shape[1])
+    X = rs.rand(*shape).astype(np.float32)
+    for biort, qshift in (("near_sym_b", "qshift_b"), ("near_sym_a", "qshift_a"), ("antonini", "qshift_06")):
+        xf = dtcwt_b200.Transform2d(biort, qshift)
+        p_tile = xf.forward(X, 1)
+        monkeypatch.setenv("DTCWT_B200_FWD_STREAM", "1")
+        with Launches() as L:
+            p_stream = xf.forward(X, 1)
+        monkeypatch.delenv("DTCWT_B200_FWD_STREAM")
+        assert L.only_fused()
+        po = O.Transform2d(coeffs.biort(biort), coeffs.qshift(qshift)).forward(X, 1)
+        assert rel_err(p_stream.lowpass, po.lowpass) < REL_TOL and rel_err(p_tile.lowpass, po.lowpass) < REL_TOL
+        assert rel_err(p_stream.highpasses[0], po.highpasses[0]) < REL_TOL
+        assert rel_err(p_stream.highpasses[0], p_tile.highpasses[0]) < REL_TOL
+
+
 @pytest.mark.parametrize("biort,qshift", [
     ("near_sym_a", "qshift_a"),      # library defaults: 5/7-tap level 1, 10-tap q-shift
     ("antonini", "qshift_06"),       # 9/7 taps zero-padded into the 13/19 instance; 10-tap q-shift
