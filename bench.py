@@ -161,7 +161,7 @@ def run_reference(args):
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, side=None, images=None):
@@ -449,7 +449,7 @@ def run_ours(args):
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
             "hbm_frac_of_measured_peak": round(ALGO_BYTES_PER_PIXEL * value * 1e6 / 1e9 / (peak * world), 4),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -508,11 +508,32 @@ def run_e2e(torch, dist, xf, pool, steps, world, dev, barrier, nimg, side):
                     "compute on side streams; PCIe-bound", "ms_per_step": round(float(ms.item()) / steps, 3)}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  NCCL and other native libraries print banners to fd 1
+    ("NCCL version ..."), so fd 1 is pointed at stderr for the whole run and the line goes to a saved copy."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
         return
+    if not (args.gpus > 1 and "WORLD_SIZE" not in os.environ):
+        claim_stdout()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: re-launch under torchrun the way the driver does
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
