@@ -105,6 +105,10 @@ typedef InvS1<7, 5, 0x7fu, 0x1fu, 8, 2> InvL1_7_5;                  // near_sym_
 // levels >= 2: q-shift pairs; every shipped family has a positive lowpass and a negative highpass tap correlation
 template <int M> struct FwdLq { typedef Fwd2d<SpecDec<M, true>, SpecDec<M, false>, 32, 16, 4> type; };
 template <int M> struct InvLq { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4> type; };
+// levels >= 2 inverse: streaming kernels for the 10- and 14-tap families (ring of 4 * (m/2 + 1) output rows)
+typedef InvSq<14, 32, 2, BakedPhase2<QshiftB_g0>, BakedPhase2<QshiftB_g1> > InvSq_qb;     // qshift_b, taps as immediates
+typedef InvSq<14, 32, 2> InvSq_14;
+typedef InvSq<10, 24, 2> InvSq_10;
 
 static int fwd_common(Fwd2dArgs& a, const float* x, float* lolo, float* yh, int64_t n, int64_t rows, int64_t cols,
                       int pr_lo, int pr_hi, int pc_lo, int pc_hi, int P, int Q, int64_t zs_n, int64_t zs_band,
@@ -253,6 +257,33 @@ int dtcwt_b200_inv2d_levelq_f32(const float* z, const float* yh, float* out, int
     if (rc) return rc;
     taps_int(a.g0, lo_a, lo_b, m, true);
     taps_int(a.g1, hi_a, hi_b, m, false);
+    if ((m == 10 || m == 14) && !env_int("DTCWT_B200_INV_TILE", 0) && cols < (1 << 27) && zs_row < (1 << 27)) {
+        InvSqArgs s;
+        s.z = z; s.yh = yh; s.out = out;
+        s.n = a.n; s.rows = a.rows; s.cols = a.cols;
+        s.crop_r = a.crop_r; s.crop_c = a.crop_c; s.out_rows = a.out_rows; s.out_cols = a.out_cols;
+        s.out_vec4 = a.out_vec4;
+        s.zs_n = zs_n; s.zs_band = zs_band; s.zs_row = zs_row;
+        for (int b = 0; b < 6; ++b) s.gain[b] = a.gain[b];
+        s.g0 = a.g0; s.g1 = a.g1;
+        for (int k = 0; k <= kStreamMaxTaps; ++k) {
+            const bool in = k < m / 2;
+            s.q[0].p[k].x = in ? a.g0.t[0][k] : 0.f; s.q[0].p[k].y = in ? a.g0.t[2][k] : 0.f;
+            s.q[1].p[k].x = in ? a.g1.t[0][k] : 0.f; s.q[1].p[k].y = in ? a.g1.t[2][k] : 0.f;
+            s.q[2].p[k].x = in ? a.g0.t[1][k] : 0.f; s.q[2].p[k].y = in ? a.g0.t[3][k] : 0.f;
+            s.q[3].p[k].x = in ? a.g1.t[1][k] : 0.f; s.q[3].p[k].y = in ? a.g1.t[3][k] : 0.f;
+        }
+        if (m == 10) {
+            s.periods = choose_periods(2 * s.rows, InvSq_10::RING, (int64_t)InvSq_10::tiles_c(s) * s.n);
+            return launch_invs1<InvSq_10>(s, stream);
+        }
+        if (BakedPhase2<QshiftB_g0>::same(s.g0) && BakedPhase2<QshiftB_g1>::same(s.g1)) {
+            s.periods = choose_periods(2 * s.rows, InvSq_qb::RING, (int64_t)InvSq_qb::tiles_c(s) * s.n);
+            return launch_invs1<InvSq_qb>(s, stream);
+        }
+        s.periods = choose_periods(2 * s.rows, InvSq_14::RING, (int64_t)InvSq_14::tiles_c(s) * s.n);
+        return launch_invs1<InvSq_14>(s, stream);
+    }
     if (m == 10) return launch_inv2d<InvLq<10>::type>(a, stream);
     if (m == 14) return launch_inv2d<InvLq<14>::type>(a, stream);
     return launch_inv2d<InvLq<18>::type>(a, stream);

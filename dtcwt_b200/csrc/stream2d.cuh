@@ -139,6 +139,16 @@ struct InvS1 {
             for (int i = 0; i < 4; ++i) { r.v[i].x = (float)q; r.v[i].y = (float)(q + i); }
             return;
         }
+#ifndef DTCWT_EMU
+        if (DBG == 3 || DBG == 4) {          // experiment: bypass L1 (ld.global.cg) / streaming hint (ld.global.cs)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2* g = reinterpret_cast<const float2*>(th.ptr[i] + (int64_t)q * th.stride[i]);
+                r.v[i] = (DBG == 3) ? __ldcg(g) : __ldcs(g);
+            }
+            return;
+        }
+#endif
 #pragma unroll
         for (int i = 0; i < 4; ++i) r.v[i] = *reinterpret_cast<const F2*>(th.ptr[i] + (int64_t)q * th.stride[i]);   // one IMAD.WIDE
     }
@@ -279,6 +289,267 @@ struct InvS1 {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if (c0 + 2 * i < a.cols) *reinterpret_cast<F2*>(d + 2 * i) = acc[i];      // cols is even
+            }
+        }
+    }
+};
+
+// =============================================================================== inverse, q-shift levels
+// Levels >= 2 of the inverse (reference transform2d.py:240-273): colifilt (lowlevel.py:156-260) interpolates 1:2, so a quad
+// row of input (2 rows) finishes 4 rows of y1 / y2.  Same streaming structure as InvS1; the ring holds m/2 groups of 4
+// output rows.  An input row of parity e feeds output phases (0, 2) of the positive-correlation filter g0 and (1, 3) of
+// the negative one g1 when e is even, and the other way round when it is odd (SpecInt::b); even rows arrive first, so
+// they carry the first touch of a group.
+struct InvSqArgs {
+    const float* z;                 // lowpass [n][rows][cols]
+    const float* yh;                // complex planar sub-bands (strides below, complex elements)
+    float* out;                     // [n][out_rows][out_cols]
+    int n, rows, cols;              // even
+    int crop_r, crop_c;             // 1: drop the first and last output row / column (transform2d.py:263-268)
+    int out_rows, out_cols;         // 2*rows - 2*crop_r, 2*cols - 2*crop_c
+    int periods;                    // emitting periods per run (a run covers RING * periods uncropped output rows)
+    int out_vec4;                   // output rows 16-byte aligned and not cropped
+    int64_t zs_n, zs_band, zs_row;
+    float gain[6];
+    PhaseTaps g0, g1;               // column pass: t[ph][k], out[4i+ph] = sum_k t[ph][k] in[2i + b(ph) + 2k]
+    PairTab q[4];                   // row pass tap pairs: (g0 phases 0,2) (g1 phases 0,2) (g0 phases 1,3) (g1 phases 1,3)
+};
+
+struct ArgPhase {
+    static DTCWT_D float get(const PhaseTaps& t, int ph, int k) { return t.t[ph][k]; }
+};
+template <class B>
+struct BakedPhase2 {
+    static DTCWT_D float get(const PhaseTaps&, int ph, int k) { return B::get(ph, k); }
+    static bool same(const PhaseTaps& t) {
+        for (int ph = 0; ph < 4; ++ph)
+            for (int k = 0; k < B::K; ++k)
+                if (!(t.t[ph][k] == B::get(ph, k))) return false;
+        return true;
+    }
+};
+
+template <int M, int RING_, int NST_, class T0 = ArgPhase, class T1 = ArgPhase>
+struct InvSq {
+    typedef InvSqArgs Args;
+    typedef SpecInt<M, true> G0;
+    typedef SpecInt<M, false> G1;
+    static constexpr int K = M / 2;                            // taps per output phase
+    static constexpr int RING = RING_, PER = RING_ / 4, NST = NST_;
+    static constexpr int HG = (K - 1) / 2;                     // groups between first touch and the input quad row
+    static constexpr int kThreads = kStreamThreads;
+    static constexpr int QC = kThreads / 2, CY = 2 * QC, CYP = CY + 4;
+    static constexpr int HC = K - 1;                           // y columns left of a strip's first input column (even)
+    static constexpr int NGR = 4;                              // groups of a row task: 8 input columns, 16 outputs
+    static constexpr int TWI = (CY - HC - (K + 1)) / (2 * NGR) * (2 * NGR);   // input columns of a strip
+    static constexpr int NSEG = TWI / (2 * NGR);
+    static constexpr int WN = round_up(2 * NGR + 2 * (K - 1), 4);              // y window of a row task
+    static constexpr int kSmemFloats = 2 * RING * CYP;
+    static constexpr int kMinBlocks = 2;
+    static_assert((K & 1) && (RING % 4) == 0 && RING >= 4 * (K + 1) && PER >= K - 1 && (PER % NST) == 0, "ring");
+    static_assert(G0::b(0) == -K + 1 && G0::b(1) == -K + 2 && G1::b(0) == -K + 2 && G1::b(1) == -K + 1, "phase pairing");
+    static_assert(WN + 2 * NGR * (NSEG - 1) <= CY, "row-pass window inside the smem row");
+
+    struct Raw { F2 v[4]; };
+    struct Thread {
+        F2 acc[RING];
+        Raw st[NST];
+        const char* ptr[4];
+        int stride[4];
+        int fc;
+    };
+
+    static DTCWT_HD int run_rows(const Args& a) { return RING * a.periods; }          // uncropped output rows per run
+    static DTCWT_HD int tiles_c(const Args& a) { return (a.cols + TWI - 1) / TWI; }
+    static DTCWT_HD int tiles_r(const Args& a) { return (2 * a.rows + run_rows(a) - 1) / run_rows(a); }
+    static DTCWT_HD int run_periods(const Args& a, int by) {
+        const int left = 2 * a.rows - run_rows(a) * by;
+        const int e = (left + RING - 1) / RING;
+        return 1 + (e < a.periods ? e : a.periods);
+    }
+    // input quad row consumed by step 0 of period p (negative above the image)
+    static DTCWT_HD int quad_base(const Args& a, int by, int p) { return run_rows(a) * by / 4 - PER + HG + PER * p; }
+    static DTCWT_HD bool edge_period(const Args& a, int bx, int by, int p) {
+        const int qb = quad_base(a, by, p);
+        return (TWI * bx - HC < 0) || (TWI * bx - HC + CY > a.cols) || qb < 0 || (qb + PER + NST > a.rows / 2);
+    }
+
+    template <bool EDGE>
+    static DTCWT_D void load_stage(const Args& a, const Thread& th, Raw& r, int q) {
+        if (EDGE) {
+            bool f;
+            q = fold_quad(q, a.rows / 2, f);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r.v[i] = *reinterpret_cast<const F2*>(th.ptr[i] + (int64_t)q * th.stride[i]);
+    }
+
+    static DTCWT_D void init(const Args& a, Thread& th, int bx, int by, int bz, int tid) {
+        const int qc = tid % QC, role = tid / QC;
+        bool fc;
+        const int gj = fold_quad((TWI * bx - HC) / 2 + qc, a.cols / 2, fc);
+        th.fc = fc ? 1 : 0;
+        const float* zimg = a.z + (int64_t)bz * a.rows * a.cols + 2 * gj;
+        const float* yb = a.yh + 2 * ((int64_t)bz * a.zs_n + gj);
+        const int sz = 8 * a.cols, sb = 8 * (int)a.zs_row;
+        const float* f[4];
+        if (role == 0) {
+            f[0] = zimg; f[1] = zimg + a.cols; f[2] = yb; f[3] = yb + 2 * 5 * a.zs_band;
+            th.stride[0] = sz; th.stride[1] = sz; th.stride[2] = sb; th.stride[3] = sb;
+        } else {
+            f[0] = yb + 2 * 2 * a.zs_band; f[1] = yb + 2 * 3 * a.zs_band;
+            f[2] = yb + 2 * 1 * a.zs_band; f[3] = yb + 2 * 4 * a.zs_band;
+            th.stride[0] = sb; th.stride[1] = sb; th.stride[2] = sb; th.stride[3] = sb;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) th.ptr[i] = reinterpret_cast<const char*>(f[i]);
+#pragma unroll
+        for (int i = 0; i < RING; ++i) th.acc[i] = zero2();
+        const int q0 = quad_base(a, by, 0);
+#pragma unroll
+        for (int s = 0; s < NST; ++s) load_stage<true>(a, th, th.st[s], q0 + s);
+    }
+
+    static DTCWT_D void c2q_rows(const F2 w0, const F2 w1, float g0, float g1, F2& top, F2& bot) {
+        const float r0 = w0.x * g0, i0 = w0.y * g0;
+        top.x = fmaf(w1.x, g1, r0); top.y = fmaf(w1.y, g1, i0);
+        bot.x = fmaf(-w1.y, g1, i0); bot.y = fmaf(w1.x, g1, -r0);
+    }
+    static DTCWT_D void flip_quad(bool fr, bool fc, F2& top, F2& bot) {
+        if (fc) { float t; t = top.x; top.x = top.y; top.y = t; t = bot.x; bot.x = bot.y; bot.y = t; }
+        if (fr) { const F2 t = top; top = bot; bot = t; }
+    }
+
+    // Input row j of the period (static) of an image filtered with spec G goes to out[2 (j - b(ph)) - 4k + ph] for the
+    // phases ph whose b(ph) has the parity of j; FIRST: the k = 0 term is the first contribution of its output row.
+    template <class G, class TS, bool FIRST>
+    static DTCWT_D void scatter(const int j, const F2 v, const PhaseTaps& t, F2 (&acc)[RING]) {
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+            if (((j - G::b(ph)) & 1) == 0) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int slot = pmod(2 * (j - G::b(ph)) - 4 * k + ph, RING);
+                    if (FIRST && k == 0) acc[slot] = fma2(TS::get(t, ph, 0), v, zero2());
+                    else acc[slot] = fma2(TS::get(t, ph, k), v, acc[slot]);
+                }
+            }
+        }
+    }
+
+    template <int ROLE, bool EDGE>
+    static DTCWT_D void cols_role(const Args& a, Thread& th, float* sm, int by, int p, int qc) {
+        const int qb = quad_base(a, by, p);
+        const bool emit = p > 0;
+        const float ga0 = a.gain[ROLE == 0 ? 0 : 2], ga1 = a.gain[ROLE == 0 ? 5 : 3];
+        const float gb0 = a.gain[1], gb1 = a.gain[4];
+        float* y = sm + ROLE * (RING * CYP) + 2 * qc;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const Raw cur = th.st[u % NST];
+            load_stage<EDGE>(a, th, th.st[u % NST], qb + u + NST);
+            F2 at, ab, bt, bb;
+            if (ROLE == 0) {
+                at = cur.v[0]; ab = cur.v[1];
+                c2q_rows(cur.v[2], cur.v[3], ga0, ga1, bt, bb);
+            } else {
+                c2q_rows(cur.v[0], cur.v[1], ga0, ga1, at, ab);
+                c2q_rows(cur.v[2], cur.v[3], gb0, gb1, bt, bb);
+            }
+            if (EDGE) {
+                bool fr;
+                fold_quad(qb + u, a.rows / 2, fr);
+                flip_quad(fr, th.fc != 0, at, ab);
+                flip_quad(fr, th.fc != 0, bt, bb);
+            }
+            // ring coordinates: input row j of the period feeds the output rows 2 (j + HGOFF) ..., see scatter()
+            scatter<G0, T0, true>(2 * u, at, a.g0, th.acc);       // even row: first touch of phases 0, 2
+            scatter<G1, T1, true>(2 * u, bt, a.g1, th.acc);       //           first touch of phases 1, 3
+            scatter<G0, T0, false>(2 * u + 1, ab, a.g0, th.acc);
+            scatter<G1, T1, false>(2 * u + 1, bb, a.g1, th.acc);
+            if (emit) {                // the group first touched K - 1 quad rows ago is complete: rows 4u .. 4u+3 of the block
+#pragma unroll
+                for (int ph = 0; ph < 4; ++ph)
+                    *reinterpret_cast<F2*>(y + (4 * u + ph) * CYP) = th.acc[pmod(4 * (u + HG - (K - 1)) + ph, RING)];
+            }
+        }
+    }
+
+    static DTCWT_D void cols(const Args& a, Thread& th, float* sm, int bx, int by, int bz, int tid, int p) {
+        const int qc = tid % QC, role = tid / QC;
+        const bool edge = edge_period(a, bx, by, p);
+        if (role == 0) {
+            if (edge) cols_role<0, true>(a, th, sm, by, p, qc);
+            else cols_role<0, false>(a, th, sm, by, p, qc);
+        } else {
+            if (edge) cols_role<1, true>(a, th, sm, by, p, qc);
+            else cols_role<1, false>(a, th, sm, by, p, qc);
+        }
+    }
+
+    // row pass of period p (p > 0): out = H:g0(y1) + H:g1(y2) on the RING rows just finished; a scalar sample times the
+    // tap pair (t[ph][k], t[ph+2][k]) advances output phases ph and ph+2 of a group in one FFMA2
+    static DTCWT_D void rows(const Args& a, float* sm, int bx, int by, int bz, int tid, int p) {
+        const float* y1 = sm;
+        const float* y2 = sm + RING * CYP;
+        float* img = a.out + (int64_t)bz * a.out_rows * a.out_cols;
+        const int r0 = run_rows(a) * by + RING * (p - 1) - a.crop_r;
+        int rp = (tid >> 1) / NSEG, seg = (tid >> 1) % NSEG;
+#pragma unroll 1
+        for (int task = tid; task < RING * NSEG; task += kThreads, rp += (kThreads / 2) / NSEG, seg += (kThreads / 2) % NSEG) {
+            if (seg >= NSEG) { seg -= NSEG; ++rp; }
+            const int yr = 2 * rp + (tid & 1);
+            const int r = r0 + yr;
+            const int c0 = 2 * (TWI * bx + 2 * NGR * seg) - a.crop_c;       // first output column of the task
+            if (r < 0 || r >= a.out_rows || c0 >= a.out_cols) continue;
+            F2 pe[NGR], po[NGR];                 // outputs (0, 2) and (1, 3) of each group
+#pragma unroll
+            for (int g = 0; g < NGR; ++g) { pe[g] = zero2(); po[g] = zero2(); }
+            const F4* s1 = reinterpret_cast<const F4*>(y1 + yr * CYP + 2 * NGR * seg);
+            const F4* s2 = reinterpret_cast<const F4*>(y2 + yr * CYP + 2 * NGR * seg);
+#pragma unroll
+            for (int c = 0; c < WN / 4; ++c) {
+                const F4 v1 = s1[c], v2 = s2[c];
+                const float w1[4] = {v1.x, v1.y, v1.z, v1.w}, w2[4] = {v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                    for (int g = 0; g < NGR; ++g) {
+                        const int num = 4 * c + i - 2 * g;
+                        if (num >= 0 && (num & 1) == 0 && num / 2 < K) {
+                            pe[g] = fma2(w1[i], a.q[0].p[num / 2], pe[g]);
+                            po[g] = fma2(w2[i], a.q[3].p[num / 2], po[g]);
+                        }
+                        if (num >= 1 && (num & 1) == 1 && (num - 1) / 2 < K) {
+                            pe[g] = fma2(w2[i], a.q[1].p[(num - 1) / 2], pe[g]);
+                            po[g] = fma2(w1[i], a.q[2].p[(num - 1) / 2], po[g]);
+                        }
+                    }
+                }
+            }
+            float o[4 * NGR];
+#pragma unroll
+            for (int g = 0; g < NGR; ++g) { o[4 * g] = pe[g].x; o[4 * g + 1] = po[g].x; o[4 * g + 2] = pe[g].y; o[4 * g + 3] = po[g].y; }
+            float* d = img + (int64_t)r * a.out_cols + c0;
+            if (a.out_vec4 && c0 + 4 * NGR <= a.out_cols) {
+#pragma unroll
+                for (int c = 0; c < NGR; ++c) {
+                    F4 v;
+                    v.x = o[4 * c]; v.y = o[4 * c + 1]; v.z = o[4 * c + 2]; v.w = o[4 * c + 3];
+                    reinterpret_cast<F4*>(d)[c] = v;
+                }
+            } else if (a.crop_c == 0) {
+#pragma unroll
+                for (int i = 0; i < 4 * NGR; i += 2)
+                    if (c0 + i < a.out_cols) {
+                        F2 v;
+                        v.x = o[i]; v.y = o[i + 1];
+                        *reinterpret_cast<F2*>(d + i) = v;
+                    }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4 * NGR; ++i)
+                    if (c0 + i >= 0 && c0 + i < a.out_cols) d[i] = o[i];
             }
         }
     }

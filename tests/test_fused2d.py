@@ -74,6 +74,8 @@ def check_roundtrip(X, biort, qshift, nlevels, gain=None, expect_fused=True):
     ((64, 1056), 2),      # wide enough for interior (no symmetric-extension) tiles of every kernel
     ((840, 48), 1),       # tall: several runs of the streaming level-1 kernels, interior periods, ragged last run
     ((410, 300), 1),      # two column strips, last period of the run partly below the image
+    ((1100, 72), 2),      # level-2 inverse streams 550 rows: two runs of the q-shift streaming kernel, 550 % 4 != 0 -> crop
+    ((160, 1000), 3),     # wide: three column strips at level 2, ragged strips at level 3
 ])
 def test_fused_vs_oracle_shapes(backend, shape, nlevels):
     rs = np.random.RandomState(shape[0] * 1000 + shape[1])
