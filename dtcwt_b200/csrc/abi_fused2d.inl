@@ -105,7 +105,7 @@ typedef InvS1<7, 5, 0x7fu, 0x1fu, 8, 2> InvL1_7_5;                  // near_sym_
 // levels >= 2: q-shift pairs; every shipped family has a positive lowpass and a negative highpass tap correlation
 template <int M> struct FwdLq { typedef Fwd2d<SpecDec<M, true>, SpecDec<M, false>, 32, 16, 4> type; };
 template <int M> struct InvLq { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4> type; };
-// levels >= 2 inverse: streaming kernels for the 10- and 14-tap families (ring of 4 * (m/2 + 1) output rows)
+// levels >= 2 inverse: streaming kernels for the 10- and 14-tap families (ring of 4 * (m/2 + 1) output rows); opt-in
 typedef InvSq<14, 32, 2, BakedPhase2<QshiftB_g0>, BakedPhase2<QshiftB_g1> > InvSq_qb;     // qshift_b, taps as immediates
 typedef InvSq<14, 32, 2> InvSq_14;
 typedef InvSq<10, 24, 2> InvSq_10;
@@ -257,7 +257,9 @@ int dtcwt_b200_inv2d_levelq_f32(const float* z, const float* yh, float* out, int
     if (rc) return rc;
     taps_int(a.g0, lo_a, lo_b, m, true);
     taps_int(a.g1, hi_a, hi_b, m, false);
-    if ((m == 10 || m == 14) && !env_int("DTCWT_B200_INV_TILE", 0) && cols < (1 << 27) && zs_row < (1 << 27)) {
+    // The streaming kernel is parity-tested but measured no faster than the tile kernel on level 2 and slower on the small
+    // levels (few, long CTAs): profiles/r1_04.  It is selected with DTCWT_B200_INV_STREAM=1.
+    if ((m == 10 || m == 14) && env_int("DTCWT_B200_INV_STREAM", 0) && cols < (1 << 27) && zs_row < (1 << 27)) {
         InvSqArgs s;
         s.z = z; s.yh = yh; s.out = out;
         s.n = a.n; s.rows = a.rows; s.cols = a.cols;

@@ -139,16 +139,6 @@ struct InvS1 {
             for (int i = 0; i < 4; ++i) { r.v[i].x = (float)q; r.v[i].y = (float)(q + i); }
             return;
         }
-#ifndef DTCWT_EMU
-        if (DBG == 3 || DBG == 4) {          // experiment: bypass L1 (ld.global.cg) / streaming hint (ld.global.cs)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2* g = reinterpret_cast<const float2*>(th.ptr[i] + (int64_t)q * th.stride[i]);
-                r.v[i] = (DBG == 3) ? __ldcg(g) : __ldcs(g);
-            }
-            return;
-        }
-#endif
 #pragma unroll
         for (int i = 0; i < 4; ++i) r.v[i] = *reinterpret_cast<const F2*>(th.ptr[i] + (int64_t)q * th.stride[i]);   // one IMAD.WIDE
     }

@@ -104,6 +104,27 @@ def test_streaming_forward_level1(backend, monkeypatch, shape):
         assert rel_err(p_stream.highpasses[0], p_tile.highpasses[0]) < REL_TOL
 
 
+@pytest.mark.parametrize("shape,nlevels", [((64, 64), 2), ((1100, 72), 2), ((160, 1000), 3), ((70, 90), 2)])
+def test_streaming_inverse_qshift(backend, monkeypatch, shape, nlevels):
+    """The streaming q-shift inverse (stream2d.cuh InvSq; the default is the tile kernel) is selected with
+    DTCWT_B200_INV_STREAM=1 and must reconstruct like the oracle, gains and crops included."""
+    rs = np.random.RandomState(shape[0] + 7 * shape[1])
+    X = rs.rand(*shape).astype(np.float32)
+    gain = rs.rand(6, nlevels)
+    for biort, qshift in (("near_sym_b", "qshift_b"), ("near_sym_a", "qshift_a")):
+        xf = dtcwt_b200.Transform2d(biort, qshift)
+        to = O.Transform2d(coeffs.biort(biort), coeffs.qshift(qshift))
+        p = xf.forward(X, nlevels)
+        monkeypatch.setenv("DTCWT_B200_INV_STREAM", "1")
+        with Launches() as L:
+            Z = npy(xf.inverse(p, gain))
+        monkeypatch.delenv("DTCWT_B200_INV_STREAM")
+        assert L.only_fused()
+        Zt = npy(xf.inverse(p, gain))
+        Zo = to.inverse(to.forward(X, nlevels), gain)
+        assert Z.shape == Zo.shape and rel_err(Z, Zo) < REL_TOL and rel_err(Z, Zt) < REL_TOL
+
+
 @pytest.mark.parametrize("biort,qshift", [
     ("near_sym_a", "qshift_a"),      # library defaults: 5/7-tap level 1, 10-tap q-shift
     ("antonini", "qshift_06"),       # 9/7 taps zero-padded into the 13/19 instance; 10-tap q-shift
