@@ -550,7 +550,7 @@ def run_3d(args):
     rank, world, local = parallel.init("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    nvol, side = 2, 256
+    nvol, side = args.images if args.images != 16 else 8, 256
     g = torch.Generator(device=dev)
     g.manual_seed(4321 + rank)
     pool = [torch.rand((nvol, side, side, side), dtype=torch.float32, device=dev, generator=g) for _ in range(3)]

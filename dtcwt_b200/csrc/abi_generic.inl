@@ -17,6 +17,26 @@ static bool load_taps(Taps<T>& t, const double* h, int m) {
 
 static bool fits_int(int64_t v) { return v >= 0 && v < (int64_t)0x3fffffff; }
 
+// Fast float32 paths (axis_pass.cuh, defined in abi_axis.inl further down the translation unit); they return
+// DTCWT_B200_EUNSUPPORTED when they decline, and there is none for float64.
+static int axis_colfilter(const float* x, float* y, int64_t outer, int64_t len, int64_t inner, int pad_lo, int pad_hi,
+                          const double* h, int m, int accumulate, void* stream);
+static int axis_coldfilt(const float* x, float* y, int64_t outer, int64_t len, int64_t inner, int pad_lo, int pad_hi,
+                         const double* ha, const double* hb, int m, int accumulate, void* stream);
+static int axis_colifilt(const float* x, float* y, int64_t outer, int64_t len, int64_t inner, int crop,
+                         const double* ha, const double* hb, int m, int accumulate, void* stream);
+static inline int axis_colfilter(const double*, double*, int64_t, int64_t, int64_t, int, int, const double*, int, int, void*) {
+    return DTCWT_B200_EUNSUPPORTED;
+}
+static inline int axis_coldfilt(const double*, double*, int64_t, int64_t, int64_t, int, int, const double*, const double*,
+                                int, int, void*) {
+    return DTCWT_B200_EUNSUPPORTED;
+}
+static inline int axis_colifilt(const double*, double*, int64_t, int64_t, int64_t, int, const double*, const double*, int,
+                                int, void*) {
+    return DTCWT_B200_EUNSUPPORTED;
+}
+
 template <typename T>
 static int colfilter_impl(const T* x, T* y, int64_t outer, int64_t len, int64_t inner, int pad_lo, int pad_hi,
                           const double* h, int m, int accumulate, void* stream) {
@@ -28,6 +48,10 @@ static int colfilter_impl(const T* x, T* y, int64_t outer, int64_t len, int64_t 
     a.len = (int)len; a.pad_lo = pad_lo; a.L = (int)len + pad_lo + pad_hi;
     a.Lout = a.L + ((m & 1) ? 0 : 1);
     a.accumulate = accumulate;
+    if (outer > 0) {
+        const int rc = axis_colfilter(x, y, outer, len, inner, pad_lo, pad_hi, h, m, accumulate, stream);
+        if (rc != DTCWT_B200_EUNSUPPORTED) return rc;
+    }
     return launch_1d<ColfilterElem<T> >(a, stream);
 }
 
@@ -50,6 +74,10 @@ static int coldfilt_impl(const T* x, T* y, int64_t outer, int64_t len, int64_t i
     a.Lout = a.L / 2;
     a.accumulate = accumulate;
     a.pos = tap_dot(ha, hb, m) > 0;
+    if (outer > 0) {
+        const int rc = axis_coldfilt(x, y, outer, len, inner, pad_lo, pad_hi, ha, hb, m, accumulate, stream);
+        if (rc != DTCWT_B200_EUNSUPPORTED) return rc;
+    }
     return launch_1d<ColdfiltElem<T> >(a, stream);
 }
 
@@ -81,6 +109,10 @@ static int colifilt_impl(const T* x, T* y, int64_t outer, int64_t len, int64_t i
     a.len = (int)len; a.crop = crop; a.Lout = 2 * (int)len - 2 * crop;
     a.accumulate = accumulate;
     colifilt_phase_tables(m, tap_dot(ha, hb, m) > 0, a.tp, a.off);
+    if (outer > 0) {
+        const int rc = axis_colifilt(x, y, outer, len, inner, crop, ha, hb, m, accumulate, stream);
+        if (rc != DTCWT_B200_EUNSUPPORTED) return rc;
+    }
     return launch_1d<ColifiltElem<T> >(a, stream);
 }
 

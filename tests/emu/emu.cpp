@@ -18,6 +18,7 @@
 #include "../../dtcwt_b200/csrc/generic_kernels.cuh"
 #include "../../dtcwt_b200/csrc/fused2d.cuh"
 #include "../../dtcwt_b200/csrc/stream2d.cuh"
+#include "../../dtcwt_b200/csrc/axis_pass.cuh"
 
 namespace dtcwt {
 
@@ -25,6 +26,13 @@ template <class Elem>
 static int launch_1d(const typename Elem::Args& a, void* /*stream*/) {
     const int64_t total = Elem::total(a);
     for (int64_t gid = 0; gid < total; ++gid) Elem::run(a, gid);
+    return DTCWT_B200_OK;
+}
+
+template <class K>
+static int launch_axis(const AxisArgs& a, void* /*stream*/) {
+    const int64_t total = K::total(a);
+    for (int64_t gid = total - 1; gid >= 0; --gid) K::run(a, gid);     // descending: exposes writes outside a thread's outputs
     return DTCWT_B200_OK;
 }
 
@@ -110,6 +118,7 @@ static int launch_fwds1(typename K::Args& a, void* /*stream*/) {
 
 #include "../../dtcwt_b200/csrc/abi_generic.inl"
 #include "../../dtcwt_b200/csrc/abi_fused2d.inl"
+#include "../../dtcwt_b200/csrc/abi_axis.inl"
 
 extern "C" {
 
