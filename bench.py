@@ -587,11 +587,11 @@ def run_3d(args):
               "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": round(ms / steps, 3), "higher_is_better": True,
               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
               "config": {"workload": "3-D DT-CWT forward+inverse, 3 levels, discard_level_1, near_sym_b+qshift_b, %d x 256^3 "
-                                     "fp32 volumes per GPU per step (BASELINE configs[3]); generic (unfused) CUDA kernels" % nvol},
+                                     "fp32 volumes per GPU per step (BASELINE configs[3]); one axis pass per launch (axis_pass.cuh), no fused 3-D level yet" % nvol},
               "gpu_launches": log.count,
               "roofline": {"bound": "hbm", "achieved": round(16.0 * value * 1e6 / 1e9 / world, 2), "peak": peak, "unit": "GB/s",
                            "frac": round(16.0 * value * 1e6 / 1e9 / world / peak, 4), "traffic": None, "peak_source": peak_src,
-                           "note": "16 B/voxel compulsory traffic (SURVEY 8(d)); whole step on the generic kernels"},
+                           "note": "16 B/voxel compulsory traffic (SURVEY 8(d)); whole step, per-axis passes"},
               "parity": {"roundtrip_max_abs_err_64cube_all_levels": err}})
     _lib.set_launch_hook(None)
 
