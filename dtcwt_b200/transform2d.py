@@ -94,32 +94,96 @@ class Transform2d(object):
         Z = self._inverse_n(Yl, Yh, t, gain_mask)
         return Z if batched else Z[0]
 
+    # data_format strings of the reference's TensorFlow backend (dtcwt/tf/transform2d.py:179-330):
+    #   "nhw" / "chw"  X [N][H][W]      -> lowpass [N][h][w],      highpasses [N][h][w][6]
+    #   "hwn" / "hwc"  X [H][W][N]      -> lowpass [h][w][N],      highpasses [h][w][N][6]
+    #   "nchw"         X [N][C][H][W]   -> lowpass [N][C][h][w],   highpasses [N][C][h][w][6]
+    #   "nhwc"         X [N][H][W][C]   -> lowpass [N][h][w][C],   highpasses [N][h][w][C][6]
+    # The kernels always see [M][H][W] (M = N or N*C) and planar [M][6][h][w] sub-bands; everything returned is a view.
+    _FORMATS_3D = ("nhw", "chw", "hwn", "hwc")
+    _FORMATS_4D = ("nchw", "nhwc")
+
+    @classmethod
+    def _check_format(cls, data_format, ndim):
+        data_format = data_format.lower()
+        if data_format not in cls._FORMATS_3D + cls._FORMATS_4D:
+            raise ValueError("The data format must be one of: {}".format(cls._FORMATS_3D + cls._FORMATS_4D))
+        if ndim != (3 if data_format in cls._FORMATS_3D else 4):
+            raise ValueError("The entered variable has incorrect shape for the specified data_format %s." % data_format)
+        return data_format
+
+    @staticmethod
+    def _to_batch(X, data_format):
+        """user layout -> ([M][H][W] contiguous, (N, C) or None)"""
+        if data_format in ("nhw", "chw"):
+            return X.contiguous(), None
+        if data_format in ("hwn", "hwc"):
+            return X.permute(2, 0, 1).contiguous(), None
+        if data_format == "nchw":
+            n, c = X.shape[:2]
+            return X.reshape((n * c,) + tuple(X.shape[2:])).contiguous(), (n, c)
+        n, c = X.shape[0], X.shape[3]                             # nhwc
+        return X.permute(0, 3, 1, 2).reshape((n * c,) + tuple(X.shape[1:3])).contiguous(), (n, c)
+
+    @staticmethod
+    def _from_batch(A, data_format, nc, trailing=0):
+        """[M][h][w](+[6]) -> user layout (a view); trailing = number of axes after (h, w)"""
+        tail = tuple(range(3, 3 + trailing))
+        if data_format in ("nhw", "chw"):
+            return A
+        if data_format in ("hwn", "hwc"):
+            return A.permute((1, 2, 0) + tail)
+        A = A.unflatten(0, nc)                                    # [N][C][h][w](+[6])
+        if data_format == "nchw":
+            return A
+        return A.permute((0, 2, 3, 1) + tuple(t + 1 for t in tail))   # nhwc
+
+    @staticmethod
+    def _to_batch_like(A, data_format, trailing=0):
+        """inverse of _from_batch for pyramids handed back by the user: -> [M][h][w](+[6])"""
+        tail = tuple(range(3, 3 + trailing))
+        if data_format in ("nhw", "chw"):
+            return A
+        if data_format in ("hwn", "hwc"):
+            return A.permute((2, 0, 1) + tail)
+        if data_format == "nhwc":
+            A = A.permute((0, 3, 1, 2) + tuple(t + 1 for t in tail))
+        return A.reshape((-1,) + tuple(A.shape[2:]))
+
     def forward_channels(self, X, data_format="nhw", nlevels=3, include_scale=False):
-        """Batched forward: X is ``[N][H][W]`` (``data_format='nhw'``) or ``[N][C][H][W]`` ('nchw')."""
+        """Batched forward transform; *data_format* as in the reference's TensorFlow backend (see above)."""
         t = self._taps()
         X = _ops.as_real_tensor(X)
-        data_format = data_format.lower()
-        if data_format == "nhw" and X.dim() == 3:
-            return self._forward_n(X, t, nlevels, include_scale)
-        if data_format == "nchw" and X.dim() == 4:
-            n, c = X.shape[:2]
-            p = self._forward_n(X.reshape((n * c,) + tuple(X.shape[2:])), t, nlevels, include_scale)
-            unf = lambda a: a.reshape((n, c) + tuple(a.shape[1:]))  # noqa: E731
-            return Pyramid(unf(p.lowpass_t), tuple(unf(h) for h in p.highpasses_t),
-                           None if p.scales_t is None else tuple(unf(s) for s in p.scales_t))
-        raise ValueError("data_format must be 'nhw' (3-D input) or 'nchw' (4-D input)")
+        data_format = self._check_format(data_format, X.dim())
+        Xb, nc = self._to_batch(X, data_format)
+        p = self._forward_n(Xb, t, nlevels, include_scale)
+        if data_format in ("nhw", "chw"):
+            return p
+        lo = self._from_batch(p.lowpass_t, data_format, nc)
+        hp = tuple(self._from_batch(h, data_format, nc, 1) for h in p.highpasses_t)
+        sc = None if p.scales_t is None else tuple(self._from_batch(s_, data_format, nc) for s_ in p.scales_t)
+        return Pyramid(lo, hp, sc)
 
     def inverse_channels(self, pyramid, data_format="nhw", gain_mask=None):
+        """Batched inverse of :meth:`forward_channels` (same *data_format*); returns the images in that layout."""
         t = self._taps()
-        data_format = data_format.lower()
-        Yl, Yh = self._pyramid_tensors(pyramid, batch_dims=2 if data_format == "nchw" else 1)
-        if data_format == "nhw" and Yl.dim() == 3:
-            return self._inverse_n(Yl, Yh, t, gain_mask)
-        if data_format == "nchw" and Yl.dim() == 4:
-            n, c = Yl.shape[:2]
-            Z = self._inverse_n(Yl.reshape((n * c,) + tuple(Yl.shape[2:])), Yh, t, gain_mask)
-            return Z.reshape((n, c) + tuple(Z.shape[1:]))
-        raise ValueError("data_format must be 'nhw' (3-D lowpass) or 'nchw' (4-D lowpass)")
+        lo = getattr(pyramid, "lowpass_t", None)
+        hs = getattr(pyramid, "highpasses_t", None)
+        if lo is None or hs is None:
+            lo, hs = pyramid.lowpass, pyramid.highpasses
+        lo = _ops.as_real_tensor(lo, "lowpass")
+        data_format = self._check_format(data_format, lo.dim())
+        nc = (lo.shape[0], lo.shape[1] if data_format == "nchw" else lo.shape[3]) if data_format in self._FORMATS_4D else None
+        Yl = self._to_batch_like(lo, data_format).contiguous()
+        planar = []
+        for h in hs:
+            h = _ops.as_complex_tensor(h, Yl.dtype)
+            if h.shape[-1] != 6:
+                raise ValueError("highpass arrays must have 6 sub-bands on their last axis")
+            h = self._to_batch_like(h, data_format, 1)             # [M][h][w][6]
+            planar.append(h.permute(0, 3, 1, 2).contiguous())      # no copy when the storage is already planar
+        Z = self._inverse_n(Yl, planar, t, gain_mask)
+        return self._from_batch(Z, data_format, nc)
 
     # ------------------------------------------------------------------ pyramid plumbing
     @staticmethod

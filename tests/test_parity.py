@@ -311,3 +311,37 @@ def test_transform3d_ext_modes_and_batch(backend):
         ps = xf.forward(B[i], 2, discard_level_1=True)
         assert np.array_equal(pb.highpasses[1][i], ps.highpasses[1])
         assert np.array_equal(Zb[i], npy(xf.inverse(ps)))
+
+
+@pytest.mark.parametrize("data_format", ["nhw", "chw", "hwn", "hwc", "nchw", "nhwc"])
+def test_forward_inverse_channels_data_formats(backend, data_format):
+    """data_format strings of the reference's TensorFlow backend (dtcwt/tf/transform2d.py:179-330): every layout gives
+    the per-image pyramids in the documented axis order and inverse_channels returns the input layout."""
+    rs = np.random.RandomState(5)
+    N, C, H, W = 2, 3, 40, 56
+    base = rs.rand(N, C, H, W).astype(np.float32)
+    xf = dtcwt_b200.Transform2d("near_sym_a", "qshift_a")
+    if data_format in ("nhw", "chw"):
+        X, pick, ax = base[:, 0], (lambda A, i, j: A[i]), [(i, 0) for i in range(N)]
+    elif data_format in ("hwn", "hwc"):
+        X, pick, ax = np.ascontiguousarray(base[:, 0].transpose(1, 2, 0)), (lambda A, i, j: A[:, :, i]), [(i, 0) for i in range(N)]
+    elif data_format == "nchw":
+        X, pick, ax = base, (lambda A, i, j: A[i, j]), [(i, j) for i in range(N) for j in range(C)]
+    else:
+        X, pick, ax = np.ascontiguousarray(base.transpose(0, 2, 3, 1)), (lambda A, i, j: A[:, :, :, j][i]), \
+            [(i, j) for i in range(N) for j in range(C)]
+    p = xf.forward_channels(X, data_format, nlevels=2, include_scale=True)
+    for i, j in ax:
+        ref = xf.forward(base[i, j], 2, include_scale=True)
+        assert np.array_equal(pick(p.lowpass, i, j), ref.lowpass)
+        for a, b in zip(p.highpasses, ref.highpasses):
+            assert np.array_equal(pick(a, i, j), b)
+        for a, b in zip(p.scales, ref.scales):
+            assert np.array_equal(pick(a, i, j), b)
+    Z = xf.inverse_channels(p, data_format)
+    Z = Z.cpu().numpy() if hasattr(Z, "cpu") else np.asarray(Z)
+    assert Z.shape == X.shape and np.abs(Z - X).max() < 1e-5
+    with pytest.raises(ValueError):
+        xf.forward_channels(X, "whn", nlevels=1)
+    with pytest.raises(ValueError):
+        xf.forward_channels(X[0], data_format, nlevels=1)
