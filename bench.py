@@ -65,6 +65,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--side", type=int, default=SIDE, help=argparse.SUPPRESS)   # debugging only
+    ap.add_argument("--biort", default=BIORT, help="level-1 family (default: the north-star pair near_sym_b/qshift_b)")
+    ap.add_argument("--qshift", default=QSHIFT)
     ap.add_argument("--workload", default="2d", choices=["2d", "3d"],
                     help="3d = BASELINE configs[3] (256^3 volumes, 3 levels, discard_level_1): informational line, "
                          "runs on the generic CUDA kernels; the headline metric is the default 2d")
@@ -597,7 +599,9 @@ def run_3d(args):
 
 
 def main():
+    global BIORT, QSHIFT
     args = parse()
+    BIORT, QSHIFT = args.biort, args.qshift
     if args.impl == "reference":
         run_reference(args)
         return
