@@ -39,10 +39,31 @@ def build(force=False, verbose=False, extra=()):
         if os.path.isfile(OUT):
             return OUT      # GPU box without a toolkit on PATH: use the library shipped in the snapshot
         raise RuntimeError("nvcc not found and %s does not exist" % OUT)
-    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-I", os.path.join(ROOT, "include"), "-o", OUT] + sources()
+    # four translation units (DTCWT_PART, csrc/common.cuh) compiled in parallel, then one link
+    objdir = os.path.join(ROOT, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f not in ("-shared",)]
+    jobs, objs = [], []
+    for src in sources():
+        for part in (0, 1, 2, 3):
+            obj = os.path.join(objdir, "%s.part%d.o" % (os.path.splitext(os.path.basename(src))[0], part))
+            cmd = [nvcc] + flags + list(extra) + ["-DDTCWT_PART=%d" % part, "-I", os.path.join(ROOT, "include"), "-c", "-o", obj, src]
+            if verbose:
+                print(" ".join(cmd))
+            jobs.append((cmd, subprocess.Popen(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+            objs.append(obj)
+    failed = False
+    for cmd, proc in jobs:
+        out, _ = proc.communicate()
+        if out and (verbose or proc.returncode):
+            print(out)
+        failed = failed or proc.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    link = [nvcc] + NVCC_FLAGS + ["-o", OUT] + objs
     if verbose:
-        print(" ".join(cmd))
-    subprocess.check_call(cmd, cwd=ROOT)
+        print(" ".join(link))
+    subprocess.check_call(link, cwd=ROOT)
     return OUT
 
 

@@ -2,6 +2,7 @@
 // preparation); the including file provides  template <class K> int launch_axis(const AxisArgs&, void* stream).
 // Every function returns DTCWT_B200_EUNSUPPORTED when it declines; the caller then runs the generic kernel.
 
+#ifdef DTCWT_EMIT_GENERIC
 namespace dtcwt {
 
 template <class F, int NG>
@@ -70,3 +71,4 @@ static int axis_colifilt(const float* x, float* y, int64_t outer, int64_t len, i
 }
 
 }  // namespace dtcwt
+#endif  // DTCWT_EMIT_GENERIC

@@ -155,6 +155,7 @@ using namespace dtcwt;
 
 extern "C" {
 
+#ifdef DTCWT_EMIT_FWD2D
 // transform2d.py:112-130 (level 1 of Transform2d.forward), 4-tuple biort
 int dtcwt_b200_fwd2d_level1_f32(const float* x, float* lolo, float* yh, int64_t n, int64_t rows, int64_t cols,
                                 int pad_r_hi, int pad_c_hi, const double* h0o, int m0, const double* h1o, int m1,
@@ -242,7 +243,9 @@ int dtcwt_b200_fwd2d_levelq_f32(const float* x, float* lolo, float* yh, int64_t 
     if (m == 14) return launch_fwd2d<FwdLq<14>::type>(a, stream);
     return launch_fwd2d<FwdLq<18>::type>(a, stream);
 }
+#endif  // DTCWT_EMIT_FWD2D
 
+#ifdef DTCWT_EMIT_INV2D_Q
 // transform2d.py:240-273 (levels >= 2 of Transform2d.inverse).  (lo_a, lo_b), (hi_a, hi_b) are colifilt's (ha, hb):
 // the reference passes (g0b, g0a) and (g1b, g1a).  gain[6] is this level's gain_mask column.
 int dtcwt_b200_inv2d_levelq_f32(const float* z, const float* yh, float* out, int64_t n, int64_t rows, int64_t cols,
@@ -290,7 +293,9 @@ int dtcwt_b200_inv2d_levelq_f32(const float* z, const float* yh, float* out, int
     if (m == 14) return launch_inv2d<InvLq<14>::type>(a, stream);
     return launch_inv2d<InvLq<18>::type>(a, stream);
 }
+#endif  // DTCWT_EMIT_INV2D_Q
 
+#ifdef DTCWT_EMIT_INV2D_1
 // transform2d.py:275-293 (level 1 of Transform2d.inverse), 4-tuple biort
 int dtcwt_b200_inv2d_level1_f32(const float* z, const float* yh, float* out, int64_t n, int64_t rows, int64_t cols,
                                 const double* g0o, int m0, const double* g1o, int m1, const double* gain,
@@ -338,5 +343,7 @@ int dtcwt_b200_inv2d_level1_f32(const float* z, const float* yh, float* out, int
     a.periods = choose_periods(a.rows, InvL1_19_19::RING, (int64_t)InvL1_19_19::tiles_c(a) * a.n);
     return launch_invs1<InvL1_19_19>(a, stream);
 }
+
+#endif  // DTCWT_EMIT_INV2D_1
 
 }  // extern "C"

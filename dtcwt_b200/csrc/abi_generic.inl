@@ -151,6 +151,7 @@ static int cube_impl(const T* src, T* dst, int64_t n, int64_t a_, int64_t b_, in
 
 using namespace dtcwt;
 
+#ifdef DTCWT_EMIT_GENERIC
 extern "C" {
 
 int dtcwt_b200_version(void) { return DTCWT_B200_VERSION; }
@@ -202,3 +203,4 @@ DTCWT_FILTERS(f64, double)
 #undef DTCWT_FILTERS
 
 }  // extern "C"
+#endif  // DTCWT_EMIT_GENERIC

@@ -7,6 +7,22 @@
 #pragma once
 #include <stdint.h>
 
+// The device library is compiled as four translation units in parallel (build.py: -DDTCWT_PART=0..3), each of which
+// emits one group of C-ABI entry points and instantiates only the kernels that group launches.  Without DTCWT_PART
+// (the host emulator, or a plain one-file nvcc build) everything is emitted.
+#if !defined(DTCWT_PART) || DTCWT_PART == 0
+#define DTCWT_EMIT_GENERIC 1          /* version / error strings, generic + per-axis filters, packers */
+#endif
+#if !defined(DTCWT_PART) || DTCWT_PART == 1
+#define DTCWT_EMIT_FWD2D 1            /* fwd2d_level1, fwd2d_levelq */
+#endif
+#if !defined(DTCWT_PART) || DTCWT_PART == 2
+#define DTCWT_EMIT_INV2D_Q 1          /* inv2d_levelq */
+#endif
+#if !defined(DTCWT_PART) || DTCWT_PART == 3
+#define DTCWT_EMIT_INV2D_1 1          /* inv2d_level1 */
+#endif
+
 #ifdef DTCWT_EMU
 #define DTCWT_HD inline
 #define DTCWT_D inline

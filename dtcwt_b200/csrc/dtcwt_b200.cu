@@ -50,6 +50,7 @@ static int launch_axis(const AxisArgs& a, void* stream) {
 #include "abi_fused2d.inl"
 #include "abi_axis.inl"
 
+#ifdef DTCWT_EMIT_GENERIC
 extern "C" {
 
 int dtcwt_b200_is_device_build(void) { return 1; }
@@ -63,3 +64,4 @@ const char* dtcwt_b200_error_string(int code) {
 }
 
 }  // extern "C"
+#endif  // DTCWT_EMIT_GENERIC
