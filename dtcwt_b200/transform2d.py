@@ -32,7 +32,7 @@ _BANDS_HL, _BANDS_LH, _BANDS_HH = (0, 5), (2, 3), (1, 4)
 
 
 def _vec(h):
-    return np.asarray(h, dtype=np.float64).reshape(-1)
+    return np.array(h, dtype=np.float64).reshape(-1)      # a private copy: it is frozen and cached
 
 
 class Transform2d(object):
@@ -52,6 +52,20 @@ class Transform2d(object):
 
     # ------------------------------------------------------------------ tap bookkeeping
     def _taps(self):
+        """Tap vectors by name; memoised per (biort, qshift) object pair and frozen, so that the launch wrappers can
+        cache their ctypes views (`biort` / `qshift` stay plain public attributes, as in the reference)."""
+        key = (id(self.biort), id(self.qshift))
+        cached = getattr(self, "_taps_cache", None)
+        if cached is not None and cached[0] == key and cached[1] is self.biort and cached[2] is self.qshift:
+            return cached[3]
+        t = self._taps_uncached()
+        for v in t.values():
+            if v is not None:
+                v.setflags(write=False)
+        self._taps_cache = (key, self.biort, self.qshift, t)
+        return t
+
+    def _taps_uncached(self):
         if len(self.biort) == 4:
             h0o, g0o, h1o, g1o = self.biort
             h2o = g2o = None
