@@ -1,0 +1,78 @@
+"""GPU-only checks at the sizes BASELINE.json names, through size-independent properties (the CPU oracle needs ~12 s per
+4096x4096 image, so it is only asked for a 1024x1024 case here): perfect reconstruction, linearity, batch = single image,
+and the oracle on a mid-size image.  Tolerance: 1e-5 relative (north star), written below."""
+import numpy as np
+import pytest
+import torch
+
+import dtcwt_b200
+import dtcwt_oracle as O
+from dtcwt_b200 import _lib, coeffs
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+@pytest.fixture(autouse=True)
+def _device_library():
+    _lib._install_emulator_for_tests(None)
+    assert _lib.lib().dtcwt_b200_is_device_build() == 1
+
+
+def test_config3_4096_roundtrip_linearity_batch():
+    """BASELINE configs[2]: 4096x4096 fp32, 4 levels, near_sym_b + qshift_b (a batch of 3 here)."""
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    X = torch.rand((3, 4096, 4096), device="cuda", generator=g)
+    xf = dtcwt_b200.Transform2d("near_sym_b", "qshift_b")
+    p = xf.forward_channels(X, "nhw", nlevels=4)
+    assert tuple(p.lowpass_t.shape) == (3, 512, 512)
+    assert [tuple(h.shape) for h in p.highpasses_t] == [(3, 2048, 2048, 6), (3, 1024, 1024, 6), (3, 512, 512, 6), (3, 256, 256, 6)]
+    Z = xf.inverse_channels(p, "nhw")
+    assert rel(Z, X) < TOL                                            # perfect reconstruction
+    # linearity: T(a x0 + b x1) = a T(x0) + b T(x1)
+    a, b = 0.75, -1.5
+    q = xf.forward_channels((a * X[0] + b * X[1]).unsqueeze(0), "nhw", nlevels=4)
+    assert rel(q.lowpass_t[0], a * p.lowpass_t[0] + b * p.lowpass_t[1]) < TOL
+    for lev in range(4):
+        want = a * p.highpasses_t[lev][0] + b * p.highpasses_t[lev][1]
+        assert rel(torch.view_as_real(q.highpasses_t[lev][0].contiguous()), torch.view_as_real(want.contiguous())) < 4 * TOL
+    # an image of a batch equals its single-image transform bit for bit
+    s = xf.forward(X[2], 4)
+    assert torch.equal(s.lowpass_t, p.lowpass_t[2])
+    assert torch.equal(s.highpasses_t[0], p.highpasses_t[0][2])
+    # the inverse is linear in the sub-bands: with gain_mask g, Z_g = Z_0 + g (Z_1 - Z_0)
+    Z0 = xf.inverse_channels(p, "nhw", gain_mask=np.zeros((6, 4)))
+    Z2 = xf.inverse_channels(p, "nhw", gain_mask=2.0 * np.ones((6, 4)))
+    assert rel(Z2 - Z0, 2.0 * (Z - Z0)) < 4 * TOL
+
+
+def test_mid_size_vs_oracle_1024():
+    rs = np.random.RandomState(3)
+    X = rs.rand(1024, 1024).astype(np.float32)
+    p = dtcwt_b200.Transform2d("near_sym_b", "qshift_b").forward(X, 4)
+    po = O.Transform2d(coeffs.biort("near_sym_b"), coeffs.qshift("qshift_b")).forward(X, 4)
+    assert np.abs(p.lowpass - po.lowpass).max() / np.abs(po.lowpass).max() < TOL
+    for a, b in zip(p.highpasses, po.highpasses):
+        assert np.abs(a - b).max() / np.abs(b).max() < TOL
+
+
+def test_config4_256cube_properties():
+    """BASELINE configs[3]: 256^3 fp32 volume, 3 levels, discard_level_1, near_sym_b + qshift_b."""
+    g = torch.Generator(device="cuda").manual_seed(4321)
+    X = torch.rand((2, 256, 256, 256), device="cuda", generator=g)
+    xf = dtcwt_b200.Transform3d("near_sym_b", "qshift_b")
+    p = xf.forward_channels(X, nlevels=3, discard_level_1=True)
+    assert p.highpasses_t[0] is None and tuple(p.lowpass_t.shape) == (2, 64, 64, 64)
+    assert tuple(p.highpasses_t[1].shape[-4:]) == (64, 64, 64, 28) and tuple(p.highpasses_t[2].shape[-4:]) == (32, 32, 32, 28)
+    a, b = 1.25, -0.5
+    q = xf.forward_channels((a * X[0] + b * X[1]).unsqueeze(0), nlevels=3, discard_level_1=True)
+    assert rel(q.lowpass_t[0], a * p.lowpass_t[0] + b * p.lowpass_t[1]) < TOL
+    want = a * p.highpasses_t[2][0] + b * p.highpasses_t[2][1]
+    assert rel(torch.view_as_real(q.highpasses_t[2][0].contiguous()), torch.view_as_real(want.contiguous())) < 4 * TOL
+    # all levels kept: perfect reconstruction of a 128^3 volume
+    Y = X[0, :128, :128, :128].contiguous()
+    assert rel(xf.inverse(xf.forward(Y, nlevels=3)), Y) < TOL
