@@ -113,7 +113,7 @@ typedef InvSq<10, 24, 2> InvSq_10;
 static int fwd_common(Fwd2dArgs& a, const float* x, float* lolo, float* yh, int64_t n, int64_t rows, int64_t cols,
                       int pr_lo, int pr_hi, int pc_lo, int pc_hi, int P, int Q, int64_t zs_n, int64_t zs_band,
                       int64_t zs_row) {
-    if (!x || !lolo || !yh || n < 0 || rows < 1 || cols < 1) return DTCWT_B200_EINVAL;
+    if (n < 0 || rows < 1 || cols < 1 || (n > 0 && (!x || !lolo || !yh))) return DTCWT_B200_EINVAL;   // an empty batch has no buffers
     if (n > 65535 || rows < kFusedMinSide || cols < kFusedMinSide || rows > (1 << 24) || cols > (1 << 24))
         return DTCWT_B200_EUNSUPPORTED;
     if (!aligned_to(lolo, 8) || !aligned_to(yh, 8) || !aligned_to(x, 4)) return DTCWT_B200_EUNSUPPORTED;
@@ -131,7 +131,8 @@ static int fwd_common(Fwd2dArgs& a, const float* x, float* lolo, float* yh, int6
 static int inv_common(Inv2dArgs& a, const float* z, const float* yh, float* out, int64_t n, int64_t rows,
                       int64_t cols, int crop_r, int crop_c, int P, int Q, const double* gain, int64_t zs_n,
                       int64_t zs_band, int64_t zs_row) {
-    if (!z || !yh || !out || !gain || n < 0 || rows < 2 || cols < 2 || (rows & 1) || (cols & 1)) return DTCWT_B200_EINVAL;
+    if (!gain || n < 0 || rows < 2 || cols < 2 || (rows & 1) || (cols & 1) || (n > 0 && (!z || !yh || !out)))
+        return DTCWT_B200_EINVAL;
     if (crop_r < 0 || crop_r > 1 || crop_c < 0 || crop_c > 1) return DTCWT_B200_EINVAL;
     if (n > 65535 || rows < kFusedMinSide || cols < kFusedMinSide || rows > (1 << 24) || cols > (1 << 24))
         return DTCWT_B200_EUNSUPPORTED;

@@ -41,7 +41,9 @@ template <typename T>
 static int colfilter_impl(const T* x, T* y, int64_t outer, int64_t len, int64_t inner, int pad_lo, int pad_hi,
                           const double* h, int m, int accumulate, void* stream) {
     ColfilterArgs<T> a;
-    if (!x || !y || outer < 0 || inner < 1 || len < 1 || pad_lo < 0 || pad_hi < 0) return DTCWT_B200_EINVAL;
+    if (outer < 0 || inner < 0 || len < 1 || pad_lo < 0 || pad_hi < 0) return DTCWT_B200_EINVAL;
+    if (outer == 0 || inner == 0) return DTCWT_B200_OK;          // empty batch / no columns: nothing to launch
+    if (!x || !y) return DTCWT_B200_EINVAL;
     if (!load_taps(a.h, h, m)) return DTCWT_B200_EINVAL;
     if (!fits_int(len + pad_lo + pad_hi + 1)) return DTCWT_B200_EUNSUPPORTED;
     a.x = x; a.y = y; a.outer = outer; a.inner = inner;
@@ -65,7 +67,9 @@ template <typename T>
 static int coldfilt_impl(const T* x, T* y, int64_t outer, int64_t len, int64_t inner, int pad_lo, int pad_hi,
                          const double* ha, const double* hb, int m, int accumulate, void* stream) {
     ColdfiltArgs<T> a;
-    if (!x || !y || outer < 0 || inner < 1 || len < 1 || pad_lo < 0 || pad_hi < 0) return DTCWT_B200_EINVAL;
+    if (outer < 0 || inner < 0 || len < 1 || pad_lo < 0 || pad_hi < 0) return DTCWT_B200_EINVAL;
+    if (outer == 0 || inner == 0) return DTCWT_B200_OK;          // empty batch / no columns: nothing to launch
+    if (!x || !y) return DTCWT_B200_EINVAL;
     if ((m & 1) || !load_taps(a.ha, ha, m) || !load_taps(a.hb, hb, m)) return DTCWT_B200_EINVAL;
     if (!fits_int(len + pad_lo + pad_hi)) return DTCWT_B200_EUNSUPPORTED;
     a.x = x; a.y = y; a.outer = outer; a.inner = inner;
@@ -101,8 +105,9 @@ template <typename T>
 static int colifilt_impl(const T* x, T* y, int64_t outer, int64_t len, int64_t inner, int crop,
                          const double* ha, const double* hb, int m, int accumulate, void* stream) {
     ColifiltArgs<T> a;
-    if (!x || !y || outer < 0 || inner < 1 || len < 2 || (len & 1) || crop < 0 || 2 * crop >= 2 * len)
-        return DTCWT_B200_EINVAL;
+    if (outer < 0 || inner < 0 || len < 2 || (len & 1) || crop < 0 || 2 * crop >= 2 * len) return DTCWT_B200_EINVAL;
+    if (outer == 0 || inner == 0) return DTCWT_B200_OK;
+    if (!x || !y) return DTCWT_B200_EINVAL;
     if ((m & 1) || !load_taps(a.ha, ha, m) || !load_taps(a.hb, hb, m)) return DTCWT_B200_EINVAL;
     if (!fits_int(2 * len)) return DTCWT_B200_EUNSUPPORTED;
     a.x = x; a.y = y; a.outer = outer; a.inner = inner;
@@ -119,7 +124,7 @@ static int colifilt_impl(const T* x, T* y, int64_t outer, int64_t len, int64_t i
 template <typename T, template <typename> class Elem>
 static int quad_impl(const T* src, T* dst, int64_t n, int64_t h, int64_t w, int64_t zs_n, int64_t zs_band,
                      int64_t zs_row, int64_t zs_col, int band0, int band1, double g0, double g1, void* stream) {
-    if (!src || !dst || n < 0 || h < 1 || w < 1 || band0 < 0 || band1 < 0) return DTCWT_B200_EINVAL;
+    if (n < 0 || h < 1 || w < 1 || band0 < 0 || band1 < 0 || (n > 0 && (!src || !dst))) return DTCWT_B200_EINVAL;
     QuadArgs<T> a;
     a.src = src; a.dst = dst; a.n = n; a.h = h; a.w = w;
     a.zs_n = zs_n; a.zs_band = zs_band; a.zs_row = zs_row; a.zs_col = zs_col;
@@ -131,7 +136,9 @@ static int quad_impl(const T* src, T* dst, int64_t n, int64_t h, int64_t w, int6
 
 template <typename T, template <typename> class Elem>
 static int pack1d_impl(const T* src, T* dst, int64_t outer, int64_t k, int64_t inner, double gain, void* stream) {
-    if (!src || !dst || outer < 0 || k < 1 || inner < 1) return DTCWT_B200_EINVAL;
+    if (outer < 0 || k < 1 || inner < 0) return DTCWT_B200_EINVAL;
+    if (outer == 0 || inner == 0) return DTCWT_B200_OK;
+    if (!src || !dst) return DTCWT_B200_EINVAL;
     Pack1dArgs<T> a;
     a.src = src; a.dst = dst; a.outer = outer; a.k = k; a.inner = inner; a.gain = (T)gain;
     return launch_1d<Elem<T> >(a, stream);
@@ -140,7 +147,7 @@ static int pack1d_impl(const T* src, T* dst, int64_t outer, int64_t k, int64_t i
 template <typename T, template <typename> class Elem>
 static int cube_impl(const T* src, T* dst, int64_t n, int64_t a_, int64_t b_, int64_t c_, int64_t zs_n,
                      int64_t zs_chan, int64_t zs_0, int64_t zs_1, int64_t zs_2, int chan0, void* stream) {
-    if (!src || !dst || n < 0 || a_ < 1 || b_ < 1 || c_ < 1 || chan0 < 0) return DTCWT_B200_EINVAL;
+    if (n < 0 || a_ < 1 || b_ < 1 || c_ < 1 || chan0 < 0 || (n > 0 && (!src || !dst))) return DTCWT_B200_EINVAL;
     CubeArgs<T> g;
     g.src = src; g.dst = dst; g.n = n; g.a = a_; g.b = b_; g.c = c_;
     g.zs_n = zs_n; g.zs_chan = zs_chan; g.zs_0 = zs_0; g.zs_1 = zs_1; g.zs_2 = zs_2; g.chan0 = chan0;

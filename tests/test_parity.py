@@ -345,3 +345,16 @@ def test_forward_inverse_channels_data_formats(backend, data_format):
         xf.forward_channels(X, "whn", nlevels=1)
     with pytest.raises(ValueError):
         xf.forward_channels(X[0], data_format, nlevels=1)
+
+
+def test_empty_batches(backend):
+    """Zero images / volumes / columns: every transform returns correctly shaped empty results without a launch."""
+    p = dtcwt_b200.Transform2d("near_sym_b", "qshift_b").forward_channels(torch.empty(0, 64, 48), "nhw", nlevels=2)
+    assert tuple(p.lowpass_t.shape) == (0, 32, 24) and [tuple(h.shape) for h in p.highpasses_t] == [(0, 32, 24, 6), (0, 16, 12, 6)]
+    assert tuple(dtcwt_b200.Transform2d("near_sym_b", "qshift_b").inverse_channels(p, "nhw").shape) == (0, 64, 48)
+    x3 = dtcwt_b200.Transform3d("near_sym_b", "qshift_b")
+    p3 = x3.forward_channels(torch.empty(0, 16, 16, 16), nlevels=2)
+    assert tuple(p3.lowpass_t.shape) == (0, 8, 8, 8) and tuple(x3.inverse(p3).shape) == (0, 16, 16, 16)
+    x1 = dtcwt_b200.Transform1d("near_sym_b", "qshift_b")
+    p1 = x1.forward(np.zeros((64, 0), np.float32), 2)
+    assert p1.lowpass.shape == (32, 0) and npy(x1.inverse(p1)).shape == (64, 0)
