@@ -533,15 +533,16 @@ struct Inv2d {
         return g;
     }
 
+    // EDGE: the tile touches the top or bottom of the image (row reflection).  Columns are handled by the caller: gj is
+    // already reflected and clamped into the image.
     template <int ROLE, bool EDGE>
-    static DTCWT_D void load_quad_row(const Args& a, const float* zimg, const float* zb, int qrow, int gj, bool okc,
-                                      Raw& r) {
+    static DTCWT_D void load_quad_row(const Args& a, const float* zimg, const float* zb, int qrow, int gj, Raw& r) {
         int gi = qrow;
         bool ok = true;
         if (EDGE) {
             bool fr;
             gi = reflect_quad(qrow, a.rows / 2, fr);
-            ok = okc && gi >= 0 && gi < a.rows / 2;
+            ok = gi >= 0 && gi < a.rows / 2;
         }
         if (EDGE && !ok) {
 #pragma unroll
@@ -577,11 +578,16 @@ struct Inv2d {
 
     template <int ROLE, bool EDGE>
     static DTCWT_D void cols_body(const Args& a, float* sm, int bx, int by, int bz, int qc, int strip) {
+        // Columns: strips on the left / right border mirror their outer quad columns (fc: swap the two columns of the
+        // quad); quad columns further out feed outputs that are never stored and are clamped.  `cedge` is uniform over the
+        // CTA, so interior strips skip the swaps with one branch -- keeping border strips on the same code as interior
+        // ones matters: a tile is only 5 strips wide at level 2 and four code variants thrash the instruction cache.
+        const bool cedge = (TWI * bx - HLC < 0) || (TWI * bx - HLC + CY > a.cols);
         int gj = (TWI * bx - HLC) / 2 + qc;                      // exact: TWI and HLC are even
-        bool fc = false, okc = true;
-        if (EDGE) {
+        bool fc = false;
+        if (cedge) {
             gj = reflect_quad(gj, a.cols / 2, fc);
-            okc = gj >= 0 && gj < a.cols / 2;
+            gj = gj < 0 ? 0 : (gj >= a.cols / 2 ? a.cols / 2 - 1 : gj);
         }
         const int qr0 = (Q * (GH * by + NGV * strip) - HLR) / 2;
         const float* zimg = a.z + (int64_t)bz * a.rows * a.cols;
@@ -592,10 +598,10 @@ struct Inv2d {
 #pragma unroll
         for (int i = 0; i < NOUT; ++i) acc[i].x = acc[i].y = 0.f;
         Raw cur, nxt;
-        load_quad_row<ROLE, EDGE>(a, zimg, zb, qr0, gj, okc, cur);
+        load_quad_row<ROLE, EDGE>(a, zimg, zb, qr0, gj, cur);
 #pragma unroll
         for (int jq = 0; jq < NQR; ++jq) {
-            if (jq + 1 < NQR) load_quad_row<ROLE, EDGE>(a, zimg, zb, qr0 + jq + 1, gj, okc, nxt);
+            if (jq + 1 < NQR) load_quad_row<ROLE, EDGE>(a, zimg, zb, qr0 + jq + 1, gj, nxt);
             F2 at, ab, bt, bb;         // image A (filtered with g0) and image B (g1): top / bottom real rows
             if (ROLE == 0) {
                 at = cur.v[0]; ab = cur.v[1];
@@ -607,8 +613,12 @@ struct Inv2d {
             if (EDGE) {
                 bool fr;
                 reflect_quad(qr0 + jq, a.rows / 2, fr);
-                flip_quad(fr, fc, at, ab);
-                flip_quad(fr, fc, bt, bb);
+                flip_quad(fr, false, at, ab);
+                flip_quad(fr, false, bt, bb);
+            }
+            if (cedge) {
+                flip_quad(false, fc, at, ab);
+                flip_quad(false, fc, bt, bb);
             }
             fir_scatter<G0, NGV, HLR>(2 * jq, at, a.g0, acc);
             fir_scatter<G1, NGV, HLR>(2 * jq, bt, a.g1, acc);
@@ -626,8 +636,7 @@ struct Inv2d {
         const int qc = tid % QCOLS;
         const int t = tid / QCOLS;
         const int role = t % 2, strip = t / 2;                   // uniform within a warp
-        const bool edge = (Q * GH * by - HLR < 0) || (Q * GH * (by + 1) + HRR > a.rows) ||
-                          (TWI * bx - HLC < 0) || (TWI * bx - HLC + CY > a.cols);
+        const bool edge = (Q * GH * by - HLR < 0) || (Q * GH * (by + 1) + HRR > a.rows);      // rows only, see cols_body
         if (role == 0) {
             if (edge) cols_body<0, true>(a, sm, bx, by, bz, qc, strip);
             else cols_body<0, false>(a, sm, bx, by, bz, qc, strip);
