@@ -125,8 +125,10 @@ struct InvS1 {
     static DTCWT_HD int quad_base(const Args& a, int by, int p) { return (run_rows(a) * by - RING + CQ) / 2 + PER * p; }
     static DTCWT_HD bool edge_period(const Args& a, int bx, int by, int p) {
         const int qb = quad_base(a, by, p);
-        return (TWI * bx - CQ < 0) || (TWI * bx - CQ + CY > a.cols) || qb < 0 || (qb + PER + NST > a.rows / 2);
+        return qb < 0 || (qb + PER + NST > a.rows / 2);           // rows only; columns: col_edge()
     }
+    // strips on the left / right border mirror their outer quad columns; uniform over the CTA
+    static DTCWT_HD bool col_edge(const Args& a, int bx) { return (TWI * bx - CQ < 0) || (TWI * bx - CQ + CY > a.cols); }
 
     template <bool EDGE>
     static DTCWT_D void load_stage(const Args& a, const Thread& th, Raw& r, int q) {
@@ -181,7 +183,7 @@ struct InvS1 {
     }
 
     template <int ROLE, bool EDGE>
-    static DTCWT_D void cols_role(const Args& a, Thread& th, float* sm, int by, int p, int qc) {
+    static DTCWT_D void cols_role(const Args& a, Thread& th, float* sm, int by, int p, int qc, bool cedge) {
         const int qb = quad_base(a, by, p);
         const bool emit = p > 0;
         const float ga0 = a.gain[ROLE == 0 ? 0 : 2], ga1 = a.gain[ROLE == 0 ? 5 : 3];
@@ -202,8 +204,12 @@ struct InvS1 {
             if (EDGE) {
                 bool fr;
                 fold_quad(qb + u, a.rows / 2, fr);
-                flip_quad(fr, th.fc != 0, at, ab);
-                flip_quad(fr, th.fc != 0, bt, bb);
+                flip_quad(fr, false, at, ab);
+                flip_quad(fr, false, bt, bb);
+            }
+            if (cedge) {
+                flip_quad(false, th.fc != 0, at, ab);
+                flip_quad(false, th.fc != 0, bt, bb);
             }
             if (DBG == 1) {
                 th.acc[pmod(2 * u - CQ, RING)].x = at.x + bt.y; th.acc[pmod(2 * u - CQ, RING)].y = at.y + bt.x;
@@ -226,13 +232,13 @@ struct InvS1 {
     // column pass of period p: consumes PER quad rows; for p > 0 leaves RING rows of y1 / y2 in shared memory
     static DTCWT_D void cols(const Args& a, Thread& th, float* sm, int bx, int by, int bz, int tid, int p) {
         const int qc = tid % QC, role = tid / QC;                // role is uniform within a warp
-        const bool edge = edge_period(a, bx, by, p);
+        const bool edge = edge_period(a, bx, by, p), cedge = col_edge(a, bx);
         if (role == 0) {
-            if (edge) cols_role<0, true>(a, th, sm, by, p, qc);
-            else cols_role<0, false>(a, th, sm, by, p, qc);
+            if (edge) cols_role<0, true>(a, th, sm, by, p, qc, cedge);
+            else cols_role<0, false>(a, th, sm, by, p, qc, cedge);
         } else {
-            if (edge) cols_role<1, true>(a, th, sm, by, p, qc);
-            else cols_role<1, false>(a, th, sm, by, p, qc);
+            if (edge) cols_role<1, true>(a, th, sm, by, p, qc, cedge);
+            else cols_role<1, false>(a, th, sm, by, p, qc, cedge);
         }
     }
 
