@@ -261,6 +261,7 @@ int dtcwt_b200_inv2d_levelq_f32(const float* z, const float* yh, float* out, int
     if (rc) return rc;
     taps_int(a.g0, lo_a, lo_b, m, true);
     taps_int(a.g1, hi_a, hi_b, m, false);
+    if (cols >= (1 << 27) || zs_row >= (1 << 27)) return DTCWT_B200_EUNSUPPORTED;   // byte strides are 32-bit
     // The streaming kernel is parity-tested but measured no faster than the tile kernel on level 2 and slower on the small
     // levels (few, long CTAs): profiles/r1_04.  It is selected with DTCWT_B200_INV_STREAM=1.
     if ((m == 10 || m == 14) && env_int("DTCWT_B200_INV_STREAM", 0) && cols < (1 << 27) && zs_row < (1 << 27)) {

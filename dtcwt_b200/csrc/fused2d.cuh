@@ -533,35 +533,22 @@ struct Inv2d {
         return g;
     }
 
-    // EDGE: the tile touches the top or bottom of the image (row reflection).  Columns are handled by the caller: gj is
-    // already reflected and clamped into the image.
-    template <int ROLE, bool EDGE>
-    static DTCWT_D void load_quad_row(const Args& a, const float* zimg, const float* zb, int qrow, int gj, Raw& r) {
+    // EDGE: the tile touches the top or bottom of the image (row reflection).  ptr[i] + qrow * stride[i] is this thread's
+    // (already column-reflected) quad column in quad row `qrow` of its four inputs: one IMAD.WIDE per load.
+    template <bool EDGE>
+    static DTCWT_D void load_quad_row(const Args& a, const char* const (&ptr)[4], const int (&stride)[4], int qrow, Raw& r) {
         int gi = qrow;
-        bool ok = true;
         if (EDGE) {
             bool fr;
             gi = reflect_quad(qrow, a.rows / 2, fr);
-            ok = gi >= 0 && gi < a.rows / 2;
-        }
-        if (EDGE && !ok) {
+            if (!(gi >= 0 && gi < a.rows / 2)) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) r.v[i].x = r.v[i].y = 0.f;
-            return;
+                for (int i = 0; i < 4; ++i) r.v[i].x = r.v[i].y = 0.f;
+                return;
+            }
         }
-        const int e = gi * (int)a.zs_row + gj;                  // the ABI guarantees 32-bit element offsets
-        if (ROLE == 0) {
-            const int ez = 2 * gi * a.cols + 2 * gj;
-            r.v[0] = *reinterpret_cast<const F2*>(zimg + ez);
-            r.v[1] = *reinterpret_cast<const F2*>(zimg + ez + a.cols);
-            r.v[2] = *reinterpret_cast<const F2*>(zb + 2 * e);
-            r.v[3] = *reinterpret_cast<const F2*>(zb + 2 * (e + 5 * (int)a.zs_band));
-        } else {
-            r.v[0] = *reinterpret_cast<const F2*>(zb + 2 * (e + 2 * (int)a.zs_band));
-            r.v[1] = *reinterpret_cast<const F2*>(zb + 2 * (e + 3 * (int)a.zs_band));
-            r.v[2] = *reinterpret_cast<const F2*>(zb + 2 * (e + 1 * (int)a.zs_band));
-            r.v[3] = *reinterpret_cast<const F2*>(zb + 2 * (e + 4 * (int)a.zs_band));
-        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r.v[i] = *reinterpret_cast<const F2*>(ptr[i] + (int64_t)gi * stride[i]);
     }
 
     // c2q (transform2d.py:324-350), gains pre-scaled by 1/sqrt2:  top row (A, B), bottom row (C, D)
@@ -590,18 +577,28 @@ struct Inv2d {
             gj = gj < 0 ? 0 : (gj >= a.cols / 2 ? a.cols / 2 - 1 : gj);
         }
         const int qr0 = (Q * (GH * by + NGV * strip) - HLR) / 2;
-        const float* zimg = a.z + (int64_t)bz * a.rows * a.cols;
-        const float* zb = a.yh + 2 * (int64_t)bz * a.zs_n;
+        const float* zimg = a.z + (int64_t)bz * a.rows * a.cols + 2 * gj;
+        const float* zb = a.yh + 2 * ((int64_t)bz * a.zs_n + gj);
+        const float* f[4];
+        if (ROLE == 0) { f[0] = zimg; f[1] = zimg + a.cols; f[2] = zb; f[3] = zb + 2 * 5 * a.zs_band; }
+        else { f[0] = zb + 2 * 2 * a.zs_band; f[1] = zb + 2 * 3 * a.zs_band; f[2] = zb + 2 * 1 * a.zs_band; f[3] = zb + 2 * 4 * a.zs_band; }
+        const char* ptr[4];
+        int stride[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            ptr[i] = reinterpret_cast<const char*>(f[i]);
+            stride[i] = (ROLE == 0 && i < 2) ? 8 * a.cols : 8 * (int)a.zs_row;      // bytes per quad row (the ABI bounds both)
+        }
         const float ga0 = a.gain[ROLE == 0 ? 0 : 2], ga1 = a.gain[ROLE == 0 ? 5 : 3];
         const float gb0 = a.gain[1], gb1 = a.gain[4];
         F2 acc[NOUT];
 #pragma unroll
         for (int i = 0; i < NOUT; ++i) acc[i].x = acc[i].y = 0.f;
         Raw cur, nxt;
-        load_quad_row<ROLE, EDGE>(a, zimg, zb, qr0, gj, cur);
+        load_quad_row<EDGE>(a, ptr, stride, qr0, cur);
 #pragma unroll
         for (int jq = 0; jq < NQR; ++jq) {
-            if (jq + 1 < NQR) load_quad_row<ROLE, EDGE>(a, zimg, zb, qr0 + jq + 1, gj, nxt);
+            if (jq + 1 < NQR) load_quad_row<EDGE>(a, ptr, stride, qr0 + jq + 1, nxt);
             F2 at, ab, bt, bb;         // image A (filtered with g0) and image B (g1): top / bottom real rows
             if (ROLE == 0) {
                 at = cur.v[0]; ab = cur.v[1];
