@@ -69,4 +69,6 @@ def build(force=False, verbose=False, extra=()):
 
 if __name__ == "__main__":
     extra = ["-Xptxas", "-v"] if "--ptxas-v" in sys.argv else []
+    if "--diagnosis" in sys.argv:      # adds the memory-only / arithmetic-only builds of InvS1 (DTCWT_B200_INV_VARIANT=1|2)
+        extra += ["-DDTCWT_DIAGNOSIS"]
     print(build(force="--force" in sys.argv or bool(extra), verbose=True, extra=extra))

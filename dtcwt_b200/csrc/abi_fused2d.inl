@@ -98,8 +98,10 @@ typedef FwdS1<19, 19, 0x7ffffu, 0x7ffffu, 20, 192, 2> FwdL1_19_19;          // a
 typedef FwdS1<5, 7, 0x1fu, 0x7fu, 8, 192, 3> FwdL1_5_7;                     // near_sym_a (+ legall 5/3)
 // level-1 inverse: streaming kernels (g0 taps, g1 taps, masks of taps that may be non-zero, ring, prefetch depth)
 typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1> > InvL1_nsb;   // near_sym_b, taps as immediates
-typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 2, 1> InvL1_nsbB;   // diagnosis: memory only
-typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 2, 2> InvL1_nsbC;   // diagnosis: arithmetic only
+#ifdef DTCWT_DIAGNOSIS     // python build.py --diagnosis: builds that give WRONG results on purpose, never part of the default library
+typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 2, 1> InvL1_nsbB;   // memory traffic only
+typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 2, 2> InvL1_nsbC;   // arithmetic only
+#endif
 typedef InvS1<19, 19, 0x7ffffu, 0x7ffffu, 24, 3> InvL1_19_19;       // any odd pair up to 19 taps (zero-padded)
 typedef InvS1<7, 5, 0x7fu, 0x1fu, 8, 2> InvL1_7_5;                  // near_sym_a (+ legall 3/5)
 // levels >= 2: q-shift pairs; every shipped family has a positive lowpass and a negative highpass tap correlation
@@ -326,6 +328,7 @@ int dtcwt_b200_inv2d_level1_f32(const float* z, const float* yh, float* out, int
         return launch_invs1<InvL1_7_5>(a, stream);
     }
     if (K1 == 13 && BakedTaps<NearSymB_g0>::same(a.g0) && BakedTaps<NearSymB_g1>::same(a.g1)) {
+#ifdef DTCWT_DIAGNOSIS
         const int variant = env_int("DTCWT_B200_INV_VARIANT", 0);
         if (variant == 1) {
             a.periods = choose_periods(a.rows, InvL1_nsbB::RING, (int64_t)InvL1_nsbB::tiles_c(a) * a.n);
@@ -335,6 +338,7 @@ int dtcwt_b200_inv2d_level1_f32(const float* z, const float* yh, float* out, int
             a.periods = choose_periods(a.rows, InvL1_nsbC::RING, (int64_t)InvL1_nsbC::tiles_c(a) * a.n);
             return launch_invs1<InvL1_nsbC>(a, stream);
         }
+#endif
         a.periods = choose_periods(a.rows, InvL1_nsb::RING, (int64_t)InvL1_nsb::tiles_c(a) * a.n);
         return launch_invs1<InvL1_nsb>(a, stream);
     }
