@@ -13,8 +13,8 @@ Prints ONE JSON line (rank 0).  See the task contract for the keys; in short
   value      device-resident throughput (CUDA events, max over ranks)
   e2e        same metric through the public API from pinned HOST buffers (H2D + D2H timed)
   roofline   dominant kernel: algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json
-  cpu_baseline  the CPU oracle (a numpy port of the reference algorithm) on the host cores
-`--impl reference` times that CPU port alone (the reference is pure numpy; it has no GPU path).
+  cpu_baseline  the unmodified reference (dtcwt.numpy from oracle/_ref) on the host cores, same image size
+`--impl reference` times that reference alone (it is pure numpy; it has no GPU path).
 """
 import argparse
 import json
@@ -73,28 +73,30 @@ def parse():
     return ap.parse_args()
 
 
-# =============================================================================== CPU oracle legs
-def _cpu_worker(job):
-    """One image forward+inverse with the CPU oracle (numpy port of the reference algorithm)."""
-    side, seed, want_detail = job
+# =============================================================================== CPU legs (the reference itself)
+# The reference's implementation of this path is single-threaded numpy (dtcwt.numpy).  oracle/build_ref.py installs
+# it, unmodified, into oracle/_ref (git-ignored, travels to the GPU box); oracle/refshim.py imports it under numpy 2.
+# When that install is missing the oracle port (oracle/dtcwt_oracle.py, ~2.7x slower) stands in and `kind` says "port".
+def cpu_kind():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refshim
+    return "reference" if refshim.available() else "port"
+
+
+def _cpu_transform():
+    """-> (Transform2d-like object of the CPU leg, kind)"""
     for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
         os.environ[v] = "1"
-    import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refshim
+    if refshim.available():
+        import logging
+        logging.disable(logging.WARNING)
+        d = refshim.load()
+        return d.numpy.Transform2d(BIORT, QSHIFT), "reference"      # dtcwt/numpy/transform2d.py:27,40,190
     import dtcwt_oracle as O
     from dtcwt_b200 import coeffs
-    X = image_for_seed(side, seed)
-    xf = O.Transform2d(coeffs.biort(BIORT), coeffs.qshift(QSHIFT))
-    t0 = time.perf_counter()
-    p = xf.forward(X, NLEVELS)
-    Z = xf.inverse(p)
-    dt = time.perf_counter() - t0
-    detail = None
-    if want_detail:
-        detail = {"Yl": p.lowpass, "Yh3": p.highpasses[3], "Yh2": p.highpasses[2],
-                  "Yh1_corner": p.highpasses[1][:64, :64].copy(), "Yh0_corner": p.highpasses[0][-64:, -64:].copy(),
-                  "Z_err": float(np.abs(Z - X).max())}
-    return dt, detail
+    return O.Transform2d(coeffs.biort(BIORT), coeffs.qshift(QSHIFT)), "port"
 
 
 def image_for_seed(side, seed):
@@ -103,22 +105,41 @@ def image_for_seed(side, seed):
     return np.random.RandomState(seed).random_sample((side, side)).astype(np.float32)
 
 
-def cpu_oracle_throughput(side, nworkers, want_detail_seed=None, repeats=1):
-    """P worker processes, one image each per repeat -> (Mpix/s aggregate, seconds, detail of worker 0)."""
+def _cpu_worker(job):
+    """One image forward+inverse on one core; with `dump` the whole pyramid and the reconstruction are saved there."""
+    side, seed, dump, names = job
+    global BIORT, QSHIFT
+    BIORT, QSHIFT = names
+    import numpy as np
+    xf, kind = _cpu_transform()
+    X = image_for_seed(side, seed)
+    t0 = time.perf_counter()
+    p = xf.forward(X, NLEVELS)
+    Z = xf.inverse(p)
+    dt = time.perf_counter() - t0
+    if dump:
+        np.save(os.path.join(dump, "Yl.npy"), np.asarray(p.lowpass, dtype=np.float32))
+        for l, h in enumerate(p.highpasses):
+            np.save(os.path.join(dump, "Yh%d.npy" % l), np.asarray(h, dtype=np.complex64))
+        np.save(os.path.join(dump, "Z.npy"), np.asarray(Z, dtype=np.float32))
+    return dt, kind
+
+
+def cpu_throughput(side, nworkers, dump_seed=None, dump_dir=None):
+    """P worker processes, one `side` x `side` image each -> (Mpix/s aggregate, seconds, kind).  Worker 0 transforms
+    the image of `dump_seed` and leaves its full pyramid in `dump_dir` for the parity check."""
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
-    jobs = [(side, 1000 + i, want_detail_seed is not None and i == 0) for i in range(nworkers)]
-    if want_detail_seed is not None:
-        jobs[0] = (side, want_detail_seed, True)
+    names = (BIORT, QSHIFT)
+    jobs = [(side, 1000 + i, None, names) for i in range(nworkers)]
+    if dump_seed is not None:
+        jobs[0] = (side, dump_seed, dump_dir, names)
     with ctx.Pool(nworkers) as pool:
-        pool.map(_cpu_worker, [(64, 1, False)] * nworkers)      # import + warm-up outside the timed part
+        pool.map(_cpu_worker, [(64, 1, None, names)] * nworkers)      # import + first call outside the timed part
         t0 = time.perf_counter()
-        res = []
-        for _ in range(repeats):
-            res = pool.map(_cpu_worker, jobs)
+        res = pool.map(_cpu_worker, jobs)
         wall = time.perf_counter() - t0
-    mpix = repeats * nworkers * side * side / wall / 1e6
-    return mpix, wall, res[0][1]
+    return nworkers * side * side / wall / 1e6, wall, res[0][1]
 
 
 def host_cores():
@@ -128,41 +149,84 @@ def host_cores():
         return max(1, os.cpu_count() or 1)
 
 
+def _ref_loop(wid, side, names, delay, q, go, stop):
+    """Reference-arm worker: forward+inverse of 4096^2 images back to back until told to stop; one token per
+    half image (after the forward, after the inverse) so the parent can place step boundaries finely."""
+    global BIORT, QSHIFT
+    BIORT, QSHIFT = names
+    xf, kind = _cpu_transform()
+    xf.inverse(xf.forward(image_for_seed(64, 1), NLEVELS))
+    X = image_for_seed(side, 1000 + wid)
+    q.put(("ready", wid, kind))
+    go.wait()
+    time.sleep(delay)
+    while not stop.is_set():
+        p = xf.forward(X, NLEVELS)
+        q.put(("half", wid, kind))
+        Z = xf.inverse(p)
+        q.put(("half", wid, kind))
+        del p, Z
+
+
 def run_reference(args):
-    """`--impl reference`: the reference's own implementation of this path is CPU numpy; it is
-    timed here through the oracle port (oracle/dtcwt_oracle.py, kind = "port") on all host cores."""
+    """`--impl reference`: the UNMODIFIED reference (dtcwt.numpy.Transform2d(...).forward/.inverse from oracle/_ref) on
+    `side` x `side` fp32 images, one single-threaded worker process per host core, all cores busy for the whole run.
+
+    The workers transform images back to back; a "step" is the completion of `n` images under that full-machine load
+    (n <= cores, chosen so that K + W steps end within a few minutes: one 4096^2 image costs 15-30 core-seconds).
+    Worker starts are staggered so completions are spread evenly and step boundaries fall on single completions."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import multiprocessing as mp
     steps = args.steps if args.steps is not None else 3
     warm = args.warmup if args.warmup is not None else 1
     cores = min(host_cores(), 64)
-    # bounded sample: one image per worker per step; image side chosen so the run ends in minutes
-    budget = 150.0 / max(1, steps + warm)
     side = args.side
-    for cand, cost in ((4096, 16.0), (2048, 4.0), (1024, 1.0), (512, 0.3)):
-        side = min(args.side, cand)
-        if cost <= budget:
-            break
-    import multiprocessing as mp
+    est_image_s = 30.0 * (side / 4096.0) ** 2                      # under load, conservative
+    n = int(cores * (240.0 / max(1, steps + warm)) / est_image_s)
+    n = max(1, min(cores, n))
     ctx = mp.get_context("spawn")
-    jobs = [(side, 1000 + i, False) for i in range(cores)]
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(64, 1, False)] * cores)
-        for _ in range(warm):
-            pool.map(_cpu_worker, jobs)
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            pool.map(_cpu_worker, jobs)
-        wall = time.perf_counter() - t0
-    value = steps * cores * side * side / wall / 1e6
-    sample = "%d worker processes x one %dx%d fp32 image per step (numpy oracle port of dtcwt.numpy)" % (cores, side, side)
+    q, go, stop = ctx.Queue(), ctx.Event(), ctx.Event()
+    names = (BIORT, QSHIFT)
+    procs = [ctx.Process(target=_ref_loop, args=(w, side, names, est_image_s * w / cores, q, go, stop), daemon=True)
+             for w in range(cores)]
+    for p in procs:
+        p.start()
+    kind = "port"
+    for _ in range(cores):
+        kind = q.get()[2]
+    go.set()
+    halves = 0
+    t0 = None
+    # the first image of every worker is ramp-up (staggered starts): it is never timed
+    skip = max(2 * warm * n, 2 * cores)
+    while True:
+        q.get()
+        halves += 1
+        if halves == skip:
+            t0 = time.perf_counter()
+        if halves == skip + 2 * steps * n:
+            t1 = time.perf_counter()
+            break
+    stop.set()
+    for p in procs:                      # mid-image workers are ended by handle (the processes started above, nothing else)
+        p.terminate()
+    for p in procs:
+        p.join(timeout=10)
+    wall = t1 - t0
+    value = steps * n * side * side / wall / 1e6
+    sample = ("unmodified reference dtcwt.numpy (oracle/_ref)" if kind == "reference" else "numpy oracle port (oracle/_ref missing)") + \
+        ": %d single-threaded worker processes transform %dx%d fp32 images back to back (forward+inverse, %d levels); " \
+        "a step = %d image(s) completed under that all-cores load; %d image(s) timed, ramp-up excluded" % (
+            cores, side, side, NLEVELS, n, steps * n)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": round(1e3 * wall / steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "images_per_step": n, "height": side, "width": side},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -366,31 +430,44 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------------------------------------------------------- parity + CPU baseline (rank 0, N=1)
+    # Image 0 of chunk 0 goes through the CPU leg (the unmodified reference when oracle/_ref exists) in one of the
+    # timed worker processes; EVERY array of its pyramid and the reconstruction are compared in full.
     parity, cpu_baseline = None, None
     if rank == 0:
         p, Z = step(0)
         torch.cuda.synchronize()
-        recon = float((Z - pool[0]).abs().max())
+        recon = float((Z - pool[0]).abs().max())              # whole chunk
         parity = {"roundtrip_max_abs_err": recon}
-        got = {"Yl": p.lowpass_t[0].cpu().numpy(), "Yh3": p.highpasses_t[3][0].cpu().numpy(),
-               "Yh2": p.highpasses_t[2][0].cpu().numpy(),
-               "Yh1_corner": p.highpasses_t[1][0, :64, :64].cpu().numpy(),
-               "Yh0_corner": p.highpasses_t[0][0, -64:, -64:].cpu().numpy()}
-        del p, Z
         if world == 1 and not args.no_cpu_baseline:
+            import shutil
+            import tempfile
+            got = {"Yl": p.lowpass_t[0].cpu().numpy(), "Z": Z[0].cpu().numpy()}
+            for l in range(NLEVELS):
+                got["Yh%d" % l] = p.highpasses_t[l][0].cpu().numpy()
+            del p, Z
             cores = min(host_cores(), 64)
-            mpix, wall, detail = cpu_oracle_throughput(side, cores, want_detail_seed=parity_seed)
-            cpu_baseline = {"value": round(mpix, 3), "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": "%d worker processes x one %dx%d fp32 image each, forward+inverse, numpy oracle "
-                                      "port of dtcwt.numpy (%.1f s wall)" % (cores, side, side, wall)}
-            worst = 0.0
-            for k, ref in detail.items():
-                if k == "Z_err":
-                    continue
-                worst = max(worst, float(np.abs(got[k] - ref).max() / np.abs(ref).max()))
-            parity.update({"vs_oracle_max_rel_err": worst, "checked": "image 0 of chunk 0: Yl, Yh[3], Yh[2], "
-                           "64x64 corners of Yh[1], Yh[0] vs CPU oracle", "tolerance": 1e-5,
-                           "ok": bool(worst < 1e-5 and recon < 1e-4)})
+            dump = tempfile.mkdtemp(prefix="dtcwt_bench_")
+            try:
+                mpix, wall, kind = cpu_throughput(side, cores, dump_seed=parity_seed, dump_dir=dump)
+                worst, per = 0.0, {}
+                for k in sorted(got):
+                    ref = np.load(os.path.join(dump, k + ".npy"))
+                    assert ref.shape == got[k].shape, (k, ref.shape, got[k].shape)
+                    per[k] = float(np.abs(got[k] - ref).max() / np.abs(ref).max())
+                    worst = max(worst, per[k])
+                    del ref
+            finally:
+                shutil.rmtree(dump, ignore_errors=True)
+            what = "unmodified reference dtcwt.numpy (oracle/_ref)" if kind == "reference" else "numpy oracle port"
+            cpu_baseline = {"value": round(mpix, 3), "unit": UNIT, "cores": cores, "kind": kind,
+                            "sample": "%d worker processes x one %dx%d fp32 image each, forward+inverse, %s (%.1f s wall)" % (
+                                cores, side, side, what, wall)}
+            parity.update({"vs_%s_max_rel_err" % kind: worst, "per_array_rel_err": {k: float("%.3g" % v) for k, v in per.items()},
+                           "checked": "image 0 of chunk 0, all arrays, all levels in full (Yl, Yh[0..%d], reconstruction) vs %s" % (
+                               NLEVELS - 1, what), "tolerance": 1e-5, "ok": bool(worst < 1e-5 and recon < 1e-4)})
+            del got
+        else:
+            del p, Z
 
     # ---------------------------------------------------------------- device-resident timing
     # Warm-up: every launch is bracketed with CUDA events (per-kernel breakdown, and which entry point dominates);

@@ -24,15 +24,30 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
-def up_to_date():
+STAMP = OUT + ".flags"      # the flag set the library was built with (a diagnosis build must never pass for the default one)
+
+
+def _flag_stamp(extra):
+    return " ".join(NVCC_FLAGS + list(extra))
+
+
+def up_to_date(extra=()):
     if not os.path.isfile(OUT):
         return False
     deps = glob.glob(os.path.join(CSRC, "*")) + [os.path.join(ROOT, "include", "dtcwt_b200.h")]
-    return all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps)
+    if not all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
+        return False
+    if _nvcc() is None:
+        return True              # GPU box without a toolkit: the shipped library is what there is
+    try:
+        with open(STAMP) as f:
+            return f.read() == _flag_stamp(extra)
+    except OSError:
+        return False
 
 
 def build(force=False, verbose=False, extra=()):
-    if not force and up_to_date():
+    if not force and up_to_date(extra):
         return OUT
     nvcc = _nvcc()
     if nvcc is None:
@@ -64,6 +79,8 @@ def build(force=False, verbose=False, extra=()):
     if verbose:
         print(" ".join(link))
     subprocess.check_call(link, cwd=ROOT)
+    with open(STAMP, "w") as f:
+        f.write(_flag_stamp(extra))
     return OUT
 
 

@@ -1,10 +1,9 @@
 """ctypes binding of ``libdtcwt_b200.so`` (the C ABI declared in ``include/dtcwt_b200.h``).
 
 There is exactly one compute path: the CUDA library.  If it has not been built,
-or no CUDA device is present, the first call raises ``RuntimeError`` -- there is
-no CPU fallback.  (``_install_emulator_for_tests`` exists so that the CPU
-test-suite can run the host logic against ``tests/emu``'s host build of the same
-kernel bodies; nothing in the package calls it.)
+is not a device build, was built against another version of the header, or no
+CUDA device is present, the first call raises ``RuntimeError`` -- there is no CPU
+fallback and no switch that selects one.
 """
 from __future__ import annotations
 
@@ -16,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdtcwt_b200.so")
 
 _LIB = None
-_EMULATED = False
+ABI_VERSION = 100       # DTCWT_B200_VERSION of include/dtcwt_b200.h this binding was written against
 
 _P, _I, _L, _D = c_void_p, c_int, c_int64, c_double
 _TAPS = ctypes.POINTER(c_double)
@@ -45,10 +44,13 @@ EXPORTS = (["dtcwt_b200_version", "dtcwt_b200_error_string", "dtcwt_b200_is_devi
            + ["dtcwt_b200_%s_f32" % n for n in _F32_ONLY])
 
 
-def _bind(path):
+def _bind(path, check_version=True):
     lib = ctypes.CDLL(path)
     lib.dtcwt_b200_version.restype = c_int
     lib.dtcwt_b200_version.argtypes = []
+    if check_version and lib.dtcwt_b200_version() != ABI_VERSION:
+        raise RuntimeError("dtcwt_b200: %s reports ABI version %d, the Python binding expects %d -- rebuild it "
+                           "(python build.py --force)" % (path, lib.dtcwt_b200_version(), ABI_VERSION))
     lib.dtcwt_b200_is_device_build.restype = c_int
     lib.dtcwt_b200_is_device_build.argtypes = []
     lib.dtcwt_b200_error_string.restype = c_char_p
@@ -78,27 +80,6 @@ def lib():
             raise RuntimeError("dtcwt_b200: %s is not a device build" % LIB_PATH)
         _LIB = loaded
     return _LIB
-
-
-def emulated():
-    return _EMULATED
-
-
-def device_type():
-    """Device type the host layer places tensors on ('cuda'; 'cpu' only under the test emulator)."""
-    return "cpu" if _EMULATED else "cuda"
-
-
-def _install_emulator_for_tests(path):
-    """TEST SEAM: route calls to tests/emu's host build of the kernel bodies."""
-    global _LIB, _EMULATED
-    if path is None:
-        _LIB, _EMULATED = None, False
-        return
-    loaded = _bind(path)
-    if loaded.dtcwt_b200_is_device_build():
-        raise RuntimeError("refusing to install a device build as the emulator")
-    _LIB, _EMULATED = loaded, True
 
 
 def check(code):

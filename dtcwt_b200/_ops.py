@@ -56,14 +56,11 @@ def as_complex_tensor(Z, real_dtype=None):
 
 
 def to_device(t):
-    kind = _lib.device_type()
-    if t.device.type == kind:
+    if t.device.type == "cuda":
         return t
-    if kind == "cuda":
-        if not torch.cuda.is_available():
-            raise RuntimeError("dtcwt_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-        return t.cuda(non_blocking=False)
-    return t.cpu()
+    if not torch.cuda.is_available():
+        raise RuntimeError("dtcwt_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return t.cuda(non_blocking=False)
 
 
 def complex_dtype(real_dtype):

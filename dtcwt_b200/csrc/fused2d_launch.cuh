@@ -254,6 +254,7 @@ static int launch_inv2d(typename K::Args& a, void* stream) {
     cudaError_t e = cudaFuncSetAttribute(inv2d_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     if (a.n == 0) return DTCWT_B200_OK;
+    if (K::tiles_r(a) > 65535 || a.n > 65535) return DTCWT_B200_EUNSUPPORTED;      // grid.y / grid.z limits
     const dim3 grid((unsigned)K::tiles_c(a), (unsigned)K::tiles_r(a), (unsigned)a.n);
     inv2d_kernel<K><<<grid, kFusedThreads, smem, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
@@ -279,6 +280,7 @@ static int launch_fwds1(typename K::Args& a, void* stream) {
         if (r == CUDA_SUCCESS) a.use_tma = 1;
     }
     if (a.n == 0) return DTCWT_B200_OK;
+    if (K::tiles_r(a) > 65535 || a.n > 65535) return DTCWT_B200_EUNSUPPORTED;      // grid.y / grid.z limits
     const dim3 grid((unsigned)K::tiles_c(a), (unsigned)K::tiles_r(a), (unsigned)a.n);
     fwds1_kernel<K><<<grid, K::kThreads, smem, (cudaStream_t)stream>>>(a, box);
     return (int)cudaGetLastError();
@@ -290,6 +292,7 @@ static int launch_invs1(typename K::Args& a, void* stream) {
     cudaError_t e = cudaFuncSetAttribute(invs1_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     if (a.n == 0) return DTCWT_B200_OK;
+    if (K::tiles_r(a) > 65535 || a.n > 65535) return DTCWT_B200_EUNSUPPORTED;      // grid.y / grid.z limits
     const dim3 grid((unsigned)K::tiles_c(a), (unsigned)K::tiles_r(a), (unsigned)a.n);
     invs1_kernel<K><<<grid, kStreamThreads, smem, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();

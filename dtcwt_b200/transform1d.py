@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _ops
 from .coeffs import biort as _biort, qshift as _qshift
-from .common import Pyramid
+from .common import Pyramid, pyramid_parts
 from .defaults import DEFAULT_BIORT, DEFAULT_QSHIFT
 
 __all__ = ["Transform1d"]
@@ -70,10 +70,7 @@ class Transform1d(object):
 
     def inverse(self, pyramid, gain_mask=None):
         t = self._taps()
-        Lo = getattr(pyramid, "lowpass_t", None)
-        Yh = getattr(pyramid, "highpasses_t", None)
-        if Lo is None or Yh is None:
-            Lo, Yh = pyramid.lowpass, pyramid.highpasses
+        Lo, Yh = pyramid_parts(pyramid)
         Lo = _ops.as_real_tensor(Lo, "lowpass")
         a = len(Yh)
         if a == 0:

@@ -21,7 +21,7 @@ import torch
 
 from . import _ops
 from .coeffs import biort as _biort, qshift as _qshift
-from .common import Pyramid
+from .common import Pyramid, pyramid_parts
 from .defaults import DEFAULT_BIORT, DEFAULT_QSHIFT
 
 __all__ = ["Transform2d"]
@@ -52,11 +52,12 @@ class Transform2d(object):
 
     # ------------------------------------------------------------------ tap bookkeeping
     def _taps(self):
-        """Tap vectors by name; memoised per (biort, qshift) object pair and frozen, so that the launch wrappers can
-        cache their ctypes views (`biort` / `qshift` stay plain public attributes, as in the reference)."""
-        key = (id(self.biort), id(self.qshift))
+        """Tap vectors by name; memoised on the CONTENT of `biort` / `qshift` (they stay plain public attributes, as in
+        the reference, so a user may replace or edit them in place) and frozen, so that the launch wrappers can cache
+        their ctypes views."""
+        key = tuple(np.asarray(h, dtype=np.float64).tobytes() for h in tuple(self.biort) + tuple(self.qshift))
         cached = getattr(self, "_taps_cache", None)
-        if cached is not None and cached[0] == key and cached[1] is self.biort and cached[2] is self.qshift:
+        if cached is not None and cached[0] == key:
             return cached[3]
         t = self._taps_uncached()
         for v in t.values():
@@ -181,10 +182,7 @@ class Transform2d(object):
     def inverse_channels(self, pyramid, data_format="nhw", gain_mask=None):
         """Batched inverse of :meth:`forward_channels` (same *data_format*); returns the images in that layout."""
         t = self._taps()
-        lo = getattr(pyramid, "lowpass_t", None)
-        hs = getattr(pyramid, "highpasses_t", None)
-        if lo is None or hs is None:
-            lo, hs = pyramid.lowpass, pyramid.highpasses
+        lo, hs = pyramid_parts(pyramid)
         lo = _ops.as_real_tensor(lo, "lowpass")
         data_format = self._check_format(data_format, lo.dim())
         nc = (lo.shape[0], lo.shape[1] if data_format == "nchw" else lo.shape[3]) if data_format in self._FORMATS_4D else None
@@ -209,10 +207,7 @@ class Transform2d(object):
     @staticmethod
     def _pyramid_tensors(pyramid, batch_dims=None):
         """-> (lowpass [N..][h][w] real, [planar highpass [M][6][h][w] complex per level])."""
-        lo = getattr(pyramid, "lowpass_t", None)
-        hs = getattr(pyramid, "highpasses_t", None)
-        if lo is None or hs is None:
-            lo, hs = pyramid.lowpass, pyramid.highpasses
+        lo, hs = pyramid_parts(pyramid)
         lo = _ops.as_real_tensor(lo, "lowpass")
         planar = []
         for h in hs:

@@ -21,7 +21,7 @@ import numpy as np
 
 from . import _ops
 from .coeffs import biort as _biort, qshift as _qshift
-from .common import Pyramid
+from .common import Pyramid, pyramid_parts
 from .defaults import DEFAULT_BIORT, DEFAULT_QSHIFT
 
 __all__ = ["Transform3d"]
@@ -81,10 +81,7 @@ class Transform3d(object):
 
     def inverse(self, pyramid):
         t = self._taps()
-        Yl = getattr(pyramid, "lowpass_t", None)
-        Yh = getattr(pyramid, "highpasses_t", None)
-        if Yl is None or Yh is None:
-            Yl, Yh = pyramid.lowpass, pyramid.highpasses
+        Yl, Yh = pyramid_parts(pyramid)
         Yl = _ops.as_real_tensor(Yl, "lowpass")
         batched = Yl.dim() == 4
         if not batched:

@@ -4,7 +4,7 @@ import sys
 import pytest
 
 ROOT = os.path.normpath(os.path.join(os.path.dirname(__file__), ".."))
-for p in (ROOT, os.path.join(ROOT, "oracle")):
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -62,11 +62,12 @@ def backend(request):
     """Run a parity test twice: on the host emulator of the kernel bodies (CPU suite) and on the
     real CUDA library (`-m gpu`).  Test code is identical; only the loaded library differs."""
     from dtcwt_b200 import _lib
+    import emu_seam
     if request.param == "emu":
-        _lib._install_emulator_for_tests(request.getfixturevalue("emulator_path"))
+        emu_seam.install(request.getfixturevalue("emulator_path"))
         yield "emu"
-        _lib._install_emulator_for_tests(None)
+        emu_seam.install(None)
     else:
-        _lib._install_emulator_for_tests(None)
+        emu_seam.install(None)
         assert _lib.lib().dtcwt_b200_is_device_build() == 1
         yield "gpu"

@@ -45,7 +45,8 @@ def test_no_cpu_fallback():
     import dtcwt_b200
     if torch.cuda.is_available():
         pytest.skip("CUDA device present")
-    _lib._install_emulator_for_tests(None)
+    import emu_seam
+    emu_seam.install(None)
     with pytest.raises(RuntimeError):
         dtcwt_b200.Transform2d().forward(np.zeros((8, 8), np.float32), 1)
 
@@ -53,9 +54,10 @@ def test_no_cpu_fallback():
 def test_emulator_cannot_masquerade(emulator_path):
     handle = ctypes.CDLL(emulator_path)
     assert handle.dtcwt_b200_is_device_build() == 0
+    import emu_seam
     with pytest.raises(RuntimeError):
-        _lib._install_emulator_for_tests(_lib.LIB_PATH)   # a device build is refused as emulator
-    _lib._install_emulator_for_tests(None)
+        emu_seam.install(_lib.LIB_PATH)   # a device build is refused as emulator
+    emu_seam.install(None)
 
 
 def test_package_does_not_import_oracle():
@@ -65,3 +67,5 @@ def test_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".inl")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "dtcwt_oracle" not in src and "refshim" not in src, f
+                if f.endswith(".py"):      # the CPU seam lives in tests/ only (the kernel bodies keep their DTCWT_EMU build)
+                    assert "emu_seam" not in src and "emulator" not in src.lower(), f

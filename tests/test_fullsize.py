@@ -19,7 +19,8 @@ def rel(a, b):
 
 @pytest.fixture(autouse=True)
 def _device_library():
-    _lib._install_emulator_for_tests(None)
+    import emu_seam
+    emu_seam.install(None)
     assert _lib.lib().dtcwt_b200_is_device_build() == 1
 
 

@@ -206,7 +206,8 @@ def test_tma_and_plain_staging_agree():
     rs = np.random.RandomState(31)
     X = rs.rand(2, 128, 256).astype(np.float32)
     xf = dtcwt_b200.Transform2d("near_sym_b", "qshift_b")
-    _lib._install_emulator_for_tests(None)
+    import emu_seam
+    emu_seam.install(None)
     p_tma = xf.forward_channels(torch.from_numpy(X).cuda(), "nhw", 2)
     # misalign the base pointer by one float so that TMA cannot be used
     buf = torch.empty(X.size + 1, dtype=torch.float32, device="cuda")

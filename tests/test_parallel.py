@@ -27,7 +27,7 @@ def _worker(rank, world, port, emu_path, q):
     try:
         os.environ.update({"RANK": str(rank), "WORLD_SIZE": str(world), "LOCAL_RANK": str(rank),
                            "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port)})
-        for p in (ROOT, os.path.join(ROOT, "oracle")):
+        for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
             if p not in sys.path:
                 sys.path.insert(0, p)
         import torch
@@ -35,7 +35,8 @@ def _worker(rank, world, port, emu_path, q):
         import dtcwt_b200
         import dtcwt_oracle as O
         from dtcwt_b200 import _lib, coeffs, parallel
-        _lib._install_emulator_for_tests(emu_path)
+        import emu_seam
+        emu_seam.install(emu_path)
         r, w, _ = parallel.init("gloo")
         assert (r, w) == (rank, world)
         # (b) rank 0 owns the real taps, the others start from garbage of the same lengths

@@ -358,3 +358,35 @@ def test_empty_batches(backend):
     x1 = dtcwt_b200.Transform1d("near_sym_b", "qshift_b")
     p1 = x1.forward(np.zeros((64, 0), np.float32), 2)
     assert p1.lowpass.shape == (32, 0) and npy(x1.inverse(p1)).shape == (64, 0)
+
+
+# ----------------------------------------------------------------------------- Pyramid: one source of truth
+def test_pyramid_numpy_edits_reach_inverse(backend, monkeypatch):
+    """Code written for the reference edits ``pyramid.highpasses[l]`` / ``.lowpass`` in place before ``inverse``
+    (reference numpy Pyramid: plain mutable attributes, dtcwt/numpy/common.py:5-32).  On a CUDA device the NumPy
+    attributes are COPIES of the device tensors; force that on the CPU run too."""
+    from dtcwt_b200 import common
+    orig = common._to_numpy
+    monkeypatch.setattr(common, "_to_numpy", lambda t: None if t is None else np.array(orig(t), copy=True))
+    X = np.random.RandomState(8).rand(64, 48).astype(np.float32)
+    xf = dtcwt_b200.Transform2d("near_sym_a", "qshift_a")
+    p = xf.forward(X, nlevels=2)
+    untouched = xf.inverse(xf.forward(X, nlevels=2)).cpu().numpy()
+    assert np.abs(untouched - X).max() < 1e-5
+    p.highpasses[0][:] = 0
+    p.lowpass[:] *= 0.5
+    want = O.Transform2d(coeffs.biort("near_sym_a"), coeffs.qshift("qshift_a"))
+    po = want.forward(X, 2)
+    po.highpasses[0][:] = 0
+    po.lowpass[:] *= 0.5
+    ref = want.inverse(po)
+    got = xf.inverse(p).cpu().numpy()
+    assert rel_err(got, ref) < REL_TOL
+    assert np.abs(got - X).max() > 1e-2            # the edit really changed the result
+    # assignment works like the reference's plain attributes, tensors or arrays
+    p.lowpass = np.zeros_like(po.lowpass)
+    p.highpasses = tuple(np.zeros_like(h) for h in po.highpasses)
+    assert float(xf.inverse(p).abs().max()) == 0.0
+    q = xf.forward(X, nlevels=2)
+    q.lowpass                                      # reading alone must not change anything
+    assert np.abs(xf.inverse(q).cpu().numpy() - X).max() < 1e-5
