@@ -629,61 +629,280 @@ def emit(line):
     out.flush()
 
 
+# =============================================================================== config 4: 3-D volumes
+METRIC_3D = "Mvoxels/s 3D DT-CWT fwd+inv 3-level discard_level_1"
+ALGO_BYTES_PER_VOXEL = 16.0      # fwd: read 4 + write Yh 3.94 + Yl 0.06; inverse the same
+SIDE_3D = 256
+# algorithmic bytes per voxel of the 256^3 input moved by each fused entry point per step: level 1 reads and
+# writes a full-size volume; levels 2 + 3 read 4 (1 + 1/8) and write their LLL + 28 complex channels
+KERNEL_ALGO_BYTES_3D = {
+    "dtcwt_b200_fwd3d_level1_lo_f32": 8.0, "dtcwt_b200_inv3d_level1_lo_f32": 8.0,
+    "dtcwt_b200_fwd3d_levelq_f32": 9.0, "dtcwt_b200_inv3d_levelq_f32": 9.0,
+}
+
+
+def _cpu_worker_3d(job):
+    """One 256^3 volume forward+inverse (3 levels, discard_level_1) with the reference on one core."""
+    side, seed, dump, names = job
+    for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[v] = "1"
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refshim
+    if refshim.available():
+        import logging
+        logging.disable(logging.WARNING)
+        xf, kind = refshim.load().numpy.Transform3d(*names), "reference"       # dtcwt/numpy/transform3d.py:22,37,133
+    else:
+        import dtcwt_oracle as O
+        from dtcwt_b200 import coeffs
+        xf, kind = O.Transform3d(coeffs.biort(names[0]), coeffs.qshift(names[1])), "port"
+    X = np.random.RandomState(seed).random_sample((side, side, side)).astype(np.float32)
+    t0 = time.perf_counter()
+    p = xf.forward(X, 3, discard_level_1=True)
+    Z = xf.inverse(p)
+    dt = time.perf_counter() - t0
+    if dump:
+        np.save(os.path.join(dump, "Yl.npy"), np.asarray(p.lowpass, dtype=np.float32))
+        for l in (1, 2):
+            np.save(os.path.join(dump, "Yh%d.npy" % l), np.asarray(p.highpasses[l], dtype=np.complex64))
+        # the reference's discard_level_1 inverse returns axes 0 and 2 exchanged (transform3d.py:452-454)
+        np.save(os.path.join(dump, "Z.npy"), np.asarray(Z, dtype=np.float32).transpose(2, 1, 0) if kind == "reference"
+                else np.asarray(Z, dtype=np.float32))
+    return dt, kind
+
+
+def run_reference_3d(args):
+    """`--impl reference --workload 3d`: the unmodified reference Transform3d on 256^3 volumes, one single-threaded
+    worker per core, a step = one volume per worker."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import multiprocessing as mp
+    steps = args.steps if args.steps is not None else 2
+    warm = args.warmup if args.warmup is not None else 1
+    cores = min(host_cores(), 64)
+    side = args.side if args.side != SIDE else SIDE_3D
+    names = (BIORT, QSHIFT)
+    ctx = mp.get_context("spawn")
+    jobs = [(side, 2000 + i, None, names) for i in range(cores)]
+    with ctx.Pool(cores) as pool:
+        kind = pool.map(_cpu_worker_3d, [(32, 1, None, names)] * cores)[0][1]
+        for _ in range(warm):
+            pool.map(_cpu_worker_3d, jobs)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_cpu_worker_3d, jobs)
+        wall = time.perf_counter() - t0
+    value = steps * cores * side ** 3 / wall / 1e6
+    sample = "%s: %d worker processes x one %d^3 fp32 volume per step, forward+inverse, 3 levels, discard_level_1" % (
+        "unmodified reference dtcwt.numpy.Transform3d (oracle/_ref)" if kind == "reference" else "numpy oracle port", cores, side)
+    emit({"impl": "reference", "metric": METRIC_3D, "value": round(value, 3), "unit": "Mvoxels/s", "n_gpus": args.gpus,
+          "steps": steps, "warmup": warm, "ms_per_step": round(1e3 * wall / steps, 3), "higher_is_better": True,
+          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_3d(args, 8, side),
+          "cpu_baseline": {"value": round(value, 3), "unit": "Mvoxels/s", "cores": cores, "kind": kind, "sample": sample},
+          "e2e": {"value": round(value, 3), "unit": "Mvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+          "gpu_launches": 0})
+
+
+def config_3d(args, nvol, side):
+    return {"workload": "3-D DT-CWT forward+inverse, 3 levels, discard_level_1, %s+%s, chunk of %d x %d^3 fp32 volumes per GPU "
+                        "per step (BASELINE configs[3])" % (BIORT, QSHIFT, nvol, side),
+            "volumes_per_gpu_per_step": nvol, "side": side, "nlevels": 3, "discard_level_1": True, "ext_mode": 4,
+            "cache": "inputs larger than L2: each step reads a %.0f MiB chunk, 3 chunks cycled" % (nvol * side ** 3 * 4 / 2 ** 20)}
+
+
 def run_3d(args):
-    """BASELINE configs[3]: 3-D forward+inverse on 256^3 fp32 volumes, 3 levels, discard_level_1, near_sym_b+qshift_b.
-    Informational (the metric of BASELINE.json is the 2-D one): Mvoxels/s, device-resident, CUDA events."""
+    """BASELINE configs[3]: 3-D forward+inverse on chunks of 256^3 fp32 volumes, 3 levels, discard_level_1,
+    near_sym_b+qshift_b: Mvoxels/s device-resident (`value`), end to end from pinned host memory (`e2e`), the dominant
+    fused entry point against the HBM roofline, the reference on the host cores beside it, full-array parity."""
+    import numpy as np
     import torch
+    import torch.distributed as dist
     import dtcwt_b200
-    from dtcwt_b200 import _lib, parallel
-    steps = args.steps if args.steps is not None else 5
-    warm = max(3, args.warmup if args.warmup is not None else 3)
+    from dtcwt_b200 import _lib, coeffs, parallel
+    steps = args.steps if args.steps is not None else 10
+    warm = max(3, args.warmup if args.warmup is not None else 5)
     rank, world, local = parallel.init("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    nvol, side = args.images if args.images != 16 else 8, 256
+    nvol = args.images if args.images != 16 else 8
+    side = args.side if args.side != SIDE else SIDE_3D
+    biort = parallel.broadcast_taps(coeffs.biort(BIORT), 0, dev)
+    qshift = parallel.broadcast_taps(coeffs.qshift(QSHIFT), 0, dev)
+    xf = dtcwt_b200.Transform3d(biort, qshift)
     g = torch.Generator(device=dev)
     g.manual_seed(4321 + rank)
     pool = [torch.rand((nvol, side, side, side), dtype=torch.float32, device=dev, generator=g) for _ in range(3)]
-    xf = dtcwt_b200.Transform3d(BIORT, QSHIFT)
-    log = LaunchLog(torch)
-    _lib.set_launch_hook(log)
+    parity_seed = 555
+    pool[0][0].copy_(torch.from_numpy(np.random.RandomState(parity_seed).random_sample((side, side, side)).astype(np.float32)))
 
     def step(i):
         p = xf.forward_channels(pool[i % 3], nlevels=3, discard_level_1=True)
-        return xf.inverse(p)
+        return p, xf.inverse(p)
 
-    # discard_level_1 drops the level-1 detail, so the timed configuration is not a perfect-reconstruction pair;
-    # parity is checked on a small volume with all levels kept (the oracle comparison lives in tests/test_parity.py)
-    small = pool[0][0, :64, :64, :64].contiguous()
-    err = float((xf.inverse(xf.forward(small, nlevels=3)) - small).abs().max())
-    step(0)
-    torch.cuda.synchronize()
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    parity, cpu_baseline = None, None
+    if rank == 0:
+        p, Z = step(0)
+        torch.cuda.synchronize()
+        if world == 1 and not args.no_cpu_baseline:
+            import multiprocessing as mp
+            import shutil
+            import tempfile
+            got = {"Yl": p.lowpass_t[0].cpu().numpy(), "Z": Z[0].cpu().numpy(),
+                   "Yh1": p.highpasses_t[1][0].cpu().numpy(), "Yh2": p.highpasses_t[2][0].cpu().numpy()}
+            del p, Z
+            cores = min(host_cores(), 64)
+            dump = tempfile.mkdtemp(prefix="dtcwt_bench3d_")
+            names = (BIORT, QSHIFT)
+            try:
+                jobs = [(side, 2000 + i, None, names) for i in range(cores)]
+                jobs[0] = (side, parity_seed, dump, names)
+                with mp.get_context("spawn").Pool(cores) as wp:
+                    wp.map(_cpu_worker_3d, [(32, 1, None, names)] * cores)
+                    t0 = time.perf_counter()
+                    res = wp.map(_cpu_worker_3d, jobs)
+                    wall = time.perf_counter() - t0
+                kind = res[0][1]
+                per = {}
+                for k in sorted(got):
+                    ref = np.load(os.path.join(dump, k + ".npy"))
+                    assert ref.shape == got[k].shape, (k, ref.shape, got[k].shape)
+                    per[k] = float(np.abs(got[k] - ref).max() / np.abs(ref).max())
+            finally:
+                shutil.rmtree(dump, ignore_errors=True)
+            what = "unmodified reference dtcwt.numpy.Transform3d (oracle/_ref)" if kind == "reference" else "numpy oracle port"
+            cpu_baseline = {"value": round(cores * side ** 3 / wall / 1e6, 3), "unit": "Mvoxels/s", "cores": cores, "kind": kind,
+                            "sample": "%d worker processes x one %d^3 fp32 volume each, forward+inverse, %s (%.1f s wall)" % (
+                                cores, side, what, wall)}
+            worst = max(per.values())
+            parity = {"vs_%s_max_rel_err" % kind: worst, "per_array_rel_err": {k: float("%.3g" % v) for k, v in per.items()},
+                      "checked": "volume 0 of chunk 0, all arrays in full (Yl, Yh[1], Yh[2], inverse) vs %s; the reference's "
+                                 "discard_level_1 inverse is transposed back (its axes 0/2 come out exchanged)" % what,
+                      "tolerance": 1e-5, "ok": bool(worst < 2e-5)}
+        else:
+            del p, Z
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.prepare()
+    log = LaunchLog(torch)
+    _lib.set_launch_hook(log)
+    log.timing = True
     for i in range(warm):
         step(i)
-    torch.cuda.synchronize()
+    barrier()
+    per_warm = log.per_kernel_ms()
+    breakdown = {k: round(v[0] / warm, 4) for k, v in sorted(per_warm.items())}
+    log.only = max(per_warm.items(), key=lambda kv: kv[1][0])[0] if per_warm else None
+    log.events = []
+    if rank == 0:
+        sampler.start()
     log.count = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     e0.record()
     for i in range(steps):
         step(warm + i)
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    barrier()
+    log.timing = False
+    launches = log.count
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    vox_rank = nvol * side ** 3
+    value = world * vox_rank * steps / (ms_total / 1e3) / 1e6
     peak, peak_src = measured_peak_gbs()
-    vox = world * nvol * side ** 3
-    value = vox * steps / (ms / 1e3) / 1e6
-    if rank == 0:
-        emit({"metric": "Mvoxels/s 3D DT-CWT fwd+inv 3-level discard_level_1", "value": round(value, 2), "unit": "Mvoxels/s",
-              "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": round(ms / steps, 3), "higher_is_better": True,
-              "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-              "config": {"workload": "3-D DT-CWT forward+inverse, 3 levels, discard_level_1, near_sym_b+qshift_b, %d x 256^3 "
-                                     "fp32 volumes per GPU per step (BASELINE configs[3]); one axis pass per launch (axis_pass.cuh), no fused 3-D level yet" % nvol},
-              "gpu_launches": log.count,
-              "roofline": {"bound": "hbm", "achieved": round(16.0 * value * 1e6 / 1e9 / world, 2), "peak": peak, "unit": "GB/s",
-                           "frac": round(16.0 * value * 1e6 / 1e9 / world / peak, 4), "traffic": None, "peak_source": peak_src,
-                           "note": "16 B/voxel compulsory traffic (SURVEY 8(d)); whole step, per-axis passes"},
-              "parity": {"roundtrip_max_abs_err_64cube_all_levels": err}})
+    roofline = None
+    per = log.per_kernel_ms()
+    if per:
+        sym, (tot_ms, n) = max(per.items(), key=lambda kv: kv[1][0])
+        per_step = n / steps
+        algo = KERNEL_ALGO_BYTES_3D.get(sym, ALGO_BYTES_PER_VOXEL) * vox_rank      # per step
+        ach = algo / (tot_ms / steps / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": sym, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "algorithmic_gb_per_step": round(algo / 1e9, 4), "launches_per_step": per_step,
+                    "note": "%s: %.1f B/voxel algorithmic per step over its %d launch(es) per step (two kernels each: slices + depth)" % (
+                        sym, KERNEL_ALGO_BYTES_3D.get(sym, ALGO_BYTES_PER_VOXEL), per_step),
+                    "ms_per_step_of_kernel": round(tot_ms / steps, 4), "share_of_step": round(tot_ms / ms_total, 4),
+                    "whole_step_frac": round(ALGO_BYTES_PER_VOXEL * vox_rank * steps / (ms_total / 1e3) / 1e9 / peak, 4),
+                    "kernels_ms_per_step": breakdown}
     _lib.set_launch_hook(None)
+
+    e2e = None
+    if not args.no_e2e:
+        def fn(x, out):
+            out.copy_(xf.inverse(xf.forward_channels(x, nlevels=3, discard_level_1=True)))
+        e2e = run_e2e_generic(torch, dist, fn, pool, steps, world, dev, barrier, (nvol, side, side, side), "Mvoxels/s")
+    if rank == 0:
+        emit({"metric": METRIC_3D, "value": round(value, 2), "unit": "Mvoxels/s", "n_gpus": world, "steps": steps, "warmup": warm,
+              "ms_per_step": round(ms_total / steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+              "dtype": "f32", "data": "synthetic", "config": config_3d(args, nvol, side), "clocks": clocks, "e2e": e2e,
+              "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity})
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e_generic(torch, dist, fn, pool, steps, world, dev, barrier, shape, unit, nbuf=3):
+    """End to end from pinned HOST memory: every step uploads its chunk (H2D), runs fn(dev_in, dev_out) and reads the
+    result back (D2H); `nbuf` chunks are in flight so the copies of neighbouring steps overlap the kernels."""
+    numel = 1
+    for v in shape:
+        numel *= v
+    host_in = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+    host_out = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+    for b in range(nbuf):
+        host_in[b].copy_(pool[b % len(pool)].cpu())
+    dev_in = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(nbuf)]
+    dev_out = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(nbuf)]
+    compute = torch.cuda.current_stream()
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    ev_in = [torch.cuda.Event() for _ in range(nbuf)]
+    ev_done = [torch.cuda.Event() for _ in range(nbuf)]
+    ev_out = [torch.cuda.Event() for _ in range(nbuf)]
+
+    def run(n):
+        for i in range(n):
+            b = i % nbuf
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_done[b])
+                dev_in[b].copy_(host_in[b], non_blocking=True)
+                ev_in[b].record(s_in)
+            compute.wait_event(ev_in[b])
+            compute.wait_event(ev_out[b])
+            fn(dev_in[b], dev_out[b])
+            ev_done[b].record(compute)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_done[b])
+                host_out[b].copy_(dev_out[b], non_blocking=True)
+                ev_out[b].record(s_out)
+        s_out.synchronize()
+
+    run(nbuf)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(steps)
+    torch.cuda.synchronize()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    val = world * numel * steps / (float(ms.item()) / 1e3) / 1e6
+    return {"value": round(val, 2), "unit": unit, "h2d_bytes_per_step": numel * 4, "d2h_bytes_per_step": numel * 4,
+            "note": "pinned host chunk -> forward -> inverse -> pinned host; %d chunks in flight, copies on side streams" % nbuf,
+            "ms_per_step": round(float(ms.item()) / steps, 3)}
 
 
 def main():
@@ -691,7 +910,10 @@ def main():
     args = parse()
     BIORT, QSHIFT = args.biort, args.qshift
     if args.impl == "reference":
-        run_reference(args)
+        if args.workload == "3d":
+            run_reference_3d(args)
+        else:
+            run_reference(args)
         return
     if not (args.gpus > 1 and "WORLD_SIZE" not in os.environ):
         claim_stdout()

@@ -54,13 +54,13 @@ def build(force=False, verbose=False, extra=()):
         if os.path.isfile(OUT):
             return OUT      # GPU box without a toolkit on PATH: use the library shipped in the snapshot
         raise RuntimeError("nvcc not found and %s does not exist" % OUT)
-    # four translation units (DTCWT_PART, csrc/common.cuh) compiled in parallel, then one link
+    # five translation units (DTCWT_PART, csrc/common.cuh) compiled in parallel, then one link
     objdir = os.path.join(ROOT, "build")
     os.makedirs(objdir, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if f not in ("-shared",)]
     jobs, objs = [], []
     for src in sources():
-        for part in (0, 1, 2, 3):
+        for part in (0, 1, 2, 3, 4):
             obj = os.path.join(objdir, "%s.part%d.o" % (os.path.splitext(os.path.basename(src))[0], part))
             cmd = [nvcc] + flags + list(extra) + ["-DDTCWT_PART=%d" % part, "-I", os.path.join(ROOT, "include"), "-c", "-o", obj, src]
             if verbose:

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdtcwt_b200.so")
 
 _LIB = None
-ABI_VERSION = 100       # DTCWT_B200_VERSION of include/dtcwt_b200.h this binding was written against
+ABI_VERSION = 200       # DTCWT_B200_VERSION of include/dtcwt_b200.h this binding was written against
 
 _P, _I, _L, _D = c_void_p, c_int, c_int64, c_double
 _TAPS = ctypes.POINTER(c_double)
@@ -37,6 +37,12 @@ _F32_ONLY = {
     "fwd2d_levelq": [_P, _P, _P, _L, _L, _L, _I, _I, _TAPS, _TAPS, _TAPS, _TAPS, _I, _L, _L, _L, _P],
     "inv2d_levelq": [_P, _P, _P, _L, _L, _L, _I, _I, _TAPS, _TAPS, _TAPS, _TAPS, _I, _TAPS, _L, _L, _L, _P],
     "inv2d_level1": [_P, _P, _P, _L, _L, _L, _TAPS, _I, _TAPS, _I, _TAPS, _L, _L, _L, _P],
+    "fwd3d_level1_lo": [_P, _P, _P, _L, _L, _L, _L, _TAPS, _I, _P],
+    "inv3d_level1_lo": [_P, _P, _P, _L, _L, _L, _L, _TAPS, _I, _P],
+    "fwd3d_level1": [_P, _P, _P, _P, _L, _L, _L, _L, _TAPS, _I, _TAPS, _I, _L, _L, _L, _L, _L, _P],
+    "inv3d_level1": [_P, _P, _P, _P, _L, _L, _L, _L, _TAPS, _I, _TAPS, _I, _L, _L, _L, _L, _L, _P],
+    "fwd3d_levelq": [_P, _P, _P, _P, _L, _L, _L, _L, _I, _I, _I, _TAPS, _TAPS, _TAPS, _TAPS, _I, _L, _L, _L, _L, _L, _P],
+    "inv3d_levelq": [_P, _P, _P, _P, _L, _L, _L, _L, _I, _I, _I, _TAPS, _TAPS, _TAPS, _TAPS, _I, _L, _L, _L, _L, _L, _P],
 }
 
 EXPORTS = (["dtcwt_b200_version", "dtcwt_b200_error_string", "dtcwt_b200_is_device_build"]

@@ -312,3 +312,96 @@ def c2cube(z, chan0):
         _lib.call("c2cube", _SUFFIX[y.dtype], _ptr(z), _ptr(y), n, a, b, c,
                   z.stride(0), z.stride(1), z.stride(2), z.stride(3), z.stride(4), chan0, _stream(z))
     return y
+
+
+# ----------------------------------------------------------------------------- fused 3-D levels
+def _chan_strides(yh):
+    return yh.stride(0), yh.stride(1), yh.stride(2), yh.stride(3), yh.stride(4)
+
+
+def lowpass3d(x, h, inverse=False):
+    """Level 1 of the 3-D transform without highpasses: colfilter(h) along all three axes of x [n][d0][d1][d2]
+    (reference transform3d.py:291-315 forward with h0o, :442-456 inverse with g0o); None when not covered."""
+    if not _fused_ok(x):
+        return None
+    n, d0, d1, d2 = x.shape
+    k, p, m = _taps(h)
+    y = torch.empty_like(x)
+    scratch = torch.empty_like(x)
+    with _on_device(x):
+        ok = _lib.call_optional("inv3d_level1_lo" if inverse else "fwd3d_level1_lo", "f32", _ptr(x), _ptr(y), _ptr(scratch),
+                                n, d0, d1, d2, p, m, _stream(x))
+    return y if ok else None
+
+
+def fwd3d_level1(x, h0o, h1o):
+    """Fused level 1 of the 3-D forward transform (reference _level1_xfm :208-289): -> (LLL, Yh planar [n][28][...])."""
+    if not _fused_ok(x):
+        return None
+    n, d0, d1, d2 = x.shape
+    if d0 % 2 or d1 % 2 or d2 % 2:
+        return None
+    k0, p0, m0 = _taps(h0o)
+    k1, p1, m1 = _taps(h1o)
+    lll = torch.empty_like(x)
+    yh = new_highpass(n, 28, (d0 // 2, d1 // 2, d2 // 2), x.dtype, x.device)
+    scratch = torch.empty((4,) + tuple(x.shape), dtype=x.dtype, device=x.device)
+    with _on_device(x):
+        ok = _lib.call_optional("fwd3d_level1", "f32", _ptr(x), _ptr(lll), _ptr(yh), _ptr(scratch), n, d0, d1, d2,
+                                p0, m0, p1, m1, *_chan_strides(yh), _stream(x))
+    return (lll, yh) if ok else None
+
+
+def fwd3d_levelq(x, lo_a, lo_b, hi_a, hi_b, pads):
+    """Fused level >= 2 of the 3-D forward transform (reference _level2_xfm :317-383); pads = replicated samples per
+    side of each axis.  -> (LLL [n][L0/2][L1/2][L2/2], Yh planar [n][28][L0/4][L1/4][L2/4]) or None."""
+    if not _fused_ok(x):
+        return None
+    n, d0, d1, d2 = x.shape
+    L = [d0 + 2 * pads[0], d1 + 2 * pads[1], d2 + 2 * pads[2]]
+    if any(v % 4 for v in L):
+        return None
+    taps = [_taps(h) for h in (lo_a, lo_b, hi_a, hi_b)]
+    if len({t[2] for t in taps}) != 1:
+        return None
+    lll = torch.empty((n, L[0] // 2, L[1] // 2, L[2] // 2), dtype=x.dtype, device=x.device)
+    yh = new_highpass(n, 28, (L[0] // 4, L[1] // 4, L[2] // 4), x.dtype, x.device)
+    scratch = torch.empty((n * d0 * L[1] * L[2],), dtype=x.dtype, device=x.device)
+    with _on_device(x):
+        ok = _lib.call_optional("fwd3d_levelq", "f32", _ptr(x), _ptr(lll), _ptr(yh), _ptr(scratch), n, d0, d1, d2,
+                                pads[0], pads[1], pads[2], taps[0][1], taps[1][1], taps[2][1], taps[3][1], taps[0][2],
+                                *_chan_strides(yh), _stream(x))
+    return (lll, yh) if ok else None
+
+
+def inv3d_levelq(yl, yh, lo_a, lo_b, hi_a, hi_b, crops):
+    """Fused level >= 2 of the 3-D inverse (reference _level2_ifm :458-526); crops = samples dropped per end of each axis."""
+    if not _fused_ok(yl, yh) or not yh.is_contiguous():
+        return None
+    n, a0, a1, a2 = yl.shape
+    taps = [_taps(h) for h in (lo_a, lo_b, hi_a, hi_b)]
+    if len({t[2] for t in taps}) != 1:
+        return None
+    od = (2 * a0 - 2 * crops[0], 2 * a1 - 2 * crops[1], 2 * a2 - 2 * crops[2])
+    out = torch.empty((n,) + od, dtype=yl.dtype, device=yl.device)
+    scratch = torch.empty((4 * n * od[0] * a1 * a2,), dtype=yl.dtype, device=yl.device)
+    with _on_device(yl):
+        ok = _lib.call_optional("inv3d_levelq", "f32", _ptr(yl), _ptr(yh), _ptr(out), _ptr(scratch), n, a0, a1, a2,
+                                crops[0], crops[1], crops[2], taps[0][1], taps[1][1], taps[2][1], taps[3][1], taps[0][2],
+                                *_chan_strides(yh), _stream(yl))
+    return out if ok else None
+
+
+def inv3d_level1(yl, yh, g0o, g1o):
+    """Fused level 1 of the 3-D inverse (reference _level1_ifm :385-440)."""
+    if not _fused_ok(yl, yh) or not yh.is_contiguous():
+        return None
+    n, a0, a1, a2 = yl.shape
+    k0, p0, m0 = _taps(g0o)
+    k1, p1, m1 = _taps(g1o)
+    out = torch.empty_like(yl)
+    scratch = torch.empty((4,) + tuple(yl.shape), dtype=yl.dtype, device=yl.device)
+    with _on_device(yl):
+        ok = _lib.call_optional("inv3d_level1", "f32", _ptr(yl), _ptr(yh), _ptr(out), _ptr(scratch), n, a0, a1, a2,
+                                p0, m0, p1, m1, *_chan_strides(yh), _stream(yl))
+    return out if ok else None

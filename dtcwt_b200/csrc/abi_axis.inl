@@ -2,7 +2,6 @@
 // preparation); the including file provides  template <class K> int launch_axis(const AxisArgs&, void* stream).
 // Every function returns DTCWT_B200_EUNSUPPORTED when it declines; the caller then runs the generic kernel.
 
-#ifdef DTCWT_EMIT_GENERIC
 namespace dtcwt {
 
 template <class F, int NG>
@@ -17,6 +16,11 @@ static bool axis_common(AxisArgs& a, const float* x, float* y, int64_t outer, in
     a.x = x; a.y = y; a.outer = outer; a.inner = (int)inner; a.len = (int)len;
     return true;
 }
+
+}  // namespace dtcwt
+
+#ifdef DTCWT_EMIT_GENERIC
+namespace dtcwt {
 
 static int axis_colfilter(const float* x, float* y, int64_t outer, int64_t len, int64_t inner, int pad_lo, int pad_hi,
                           const double* h, int m, int accumulate, void* stream) {

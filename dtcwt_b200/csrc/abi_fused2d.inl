@@ -36,14 +36,14 @@ static void taps_dec(PhaseTaps& t, const double* ha, const double* hb, int m, bo
 
 // colifilt (lowlevel.py:205-258): Y[4i+ph] = sum_k f_ph[2k + tp_ph] X[2i + m2 - 2k + off_ph], f_ph = hb for odd ph.
 // Reversed: t[ph][k'] = f_ph[2(m2-1-k') + tp_ph], in[2i - m2 + 2 + off_ph + 2k'].
-static void taps_int(PhaseTaps& t, const double* ha, const double* hb, int m, bool pos) {
+static void taps_int(PhaseTaps& t, const double* ha, const double* hb, int m, bool pos, double scale = 1.0) {
     clear_taps(t);
     int tp[4], off[4];
     colifilt_phase_tables(m, pos, tp, off);
     const int m2 = m / 2;
     for (int ph = 0; ph < 4; ++ph) {
         const double* f = (ph & 1) ? hb : ha;
-        for (int k = 0; k < m2; ++k) t.t[ph][k] = (float)f[2 * (m2 - 1 - k) + tp[ph]];
+        for (int k = 0; k < m2; ++k) t.t[ph][k] = (float)((double)(float)f[2 * (m2 - 1 - k) + tp[ph]] * scale);
     }
 }
 

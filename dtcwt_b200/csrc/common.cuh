@@ -7,7 +7,7 @@
 #pragma once
 #include <stdint.h>
 
-// The device library is compiled as four translation units in parallel (build.py: -DDTCWT_PART=0..3), each of which
+// The device library is compiled as four translation units in parallel (build.py: -DDTCWT_PART=0..4), each of which
 // emits one group of C-ABI entry points and instantiates only the kernels that group launches.  Without DTCWT_PART
 // (the host emulator, or a plain one-file nvcc build) everything is emitted.
 #if !defined(DTCWT_PART) || DTCWT_PART == 0
@@ -21,6 +21,9 @@
 #endif
 #if !defined(DTCWT_PART) || DTCWT_PART == 3
 #define DTCWT_EMIT_INV2D_1 1          /* inv2d_level1 */
+#endif
+#if !defined(DTCWT_PART) || DTCWT_PART == 4
+#define DTCWT_EMIT_FUSED3D 1          /* fwd3d_*, inv3d_* */
 #endif
 
 #ifdef DTCWT_EMU

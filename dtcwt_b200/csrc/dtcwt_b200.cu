@@ -4,6 +4,7 @@
 
 #include "generic_kernels.cuh"
 #include "fused2d.cuh"
+#include "fused3d.cuh"
 #include "axis_pass.cuh"
 
 namespace dtcwt {
@@ -43,12 +44,30 @@ static int launch_axis(const AxisArgs& a, void* stream) {
     return (int)cudaGetLastError();
 }
 
+// depth passes of the fused 3-D levels (fused3d.cuh): one thread per (2 x 2 patch, depth group, image, volume)
+template <class K>
+__global__ void __launch_bounds__(256) z3_kernel(const __grid_constant__ Z3Args a, const int64_t total) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < total) K::run(a, gid);
+}
+
+template <class K>
+static int launch_z3(const Z3Args& a, void* stream) {
+    const int64_t total = K::total(a);
+    if (total <= 0) return DTCWT_B200_OK;
+    const int64_t blocks = (total + 255) / 256;
+    if (blocks > 0x7fffffffLL) return DTCWT_B200_EUNSUPPORTED;
+    z3_kernel<K><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, total);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace dtcwt
 
 #include "abi_generic.inl"
 #include "fused2d_launch.cuh"
 #include "abi_fused2d.inl"
 #include "abi_axis.inl"
+#include "abi_fused3d.inl"
 
 #ifdef DTCWT_EMIT_GENERIC
 extern "C" {

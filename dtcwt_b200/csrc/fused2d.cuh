@@ -204,9 +204,19 @@ struct Fwd2dArgs {
     PairTab ph0, ph1s;              // level 1 only: the row-pass taps as pairs (t[k], t[k-1]) for the packed row pass
 };
 
-template <class H0, class H1, int GH_, int GW_, int NGV_, class TV0 = RtPhase, class TV1S = RtPhase, class TV1 = RtPhase>
+// MODE: what leaves the column pass
+//   kFwdQ2c   (2-D transform)  LoLo + the six complex sub-bands (q2c in registers)
+//   kFwdRaw   (3-D transform, x/y passes of one slice; transform3d.py:256-273, 353-369)  the four REAL images
+//             s0 = V:h0 H:h0, s1 = V:h1 H:h0, s2 = V:h0 H:h1, s3 = V:h1 H:h1, image s at lolo + s * zs_band (floats);
+//             the host passes unscaled taps (the packers' scale belongs to cube2c, fused3d.cuh)
+//   kFwdLow   (3-D level 1 without highpasses, transform3d.py:291-315, 442-456)  V:h0 H:h0 only
+constexpr int kFwdQ2c = 0, kFwdRaw = 1, kFwdLow = 2;
+
+template <class H0, class H1, int GH_, int GW_, int NGV_, class TV0 = RtPhase, class TV1S = RtPhase, class TV1 = RtPhase,
+          int MODE_ = kFwdQ2c>
 struct Fwd2d {
     typedef Fwd2dArgs Args;
+    static constexpr int MODE = MODE_;
     static constexpr int P = H0::P, Q = H0::Q;
     static constexpr int GH = GH_, GW = GW_, NGV = NGV_;
     static constexpr int NGH = 4 / Q;                       // a row task covers 4 input columns
@@ -222,7 +232,7 @@ struct Fwd2d {
     static constexpr int NSEG = GW / NGH;
     static constexpr int NR = Q * NGV + HL + HR;            // input rows of a column task
     static constexpr int NOUT = P * NGV;                    // output rows of a column task (even)
-    static constexpr int kSmemFloats = RX * CX + 2 * RX * CA;
+    static constexpr int kSmemFloats = RX * CX + (MODE == kFwdLow ? 1 : 2) * RX * CA;
     static constexpr int kThreads = kFusedThreads;
     static constexpr int kPhases = 5;
     // q-shift levels: one resident wave of CTAs walks over the tiles and prefetches the next tile during the column
@@ -299,13 +309,13 @@ struct Fwd2d {
             for (int c = 0; c < WN / 4; ++c) {
                 const F4 v = src[c];
                 pair_gather4<H0::K, H0::MASK, C0, -HLA, 4, WN>(4 * c, v, a.ph0, oa);
-                pair_gather4<H1::K, H1::MASK, C1, -HLA, 4, WN>(4 * c, v, a.ph1s, ob);
+                if (MODE != kFwdLow) pair_gather4<H1::K, H1::MASK, C1, -HLA, 4, WN>(4 * c, v, a.ph1s, ob);
             }
             F4 va, vb;
             va.x = oa[0].x; va.y = oa[0].y; va.z = oa[1].x; va.w = oa[1].y;
             vb.x = ob[0].x; vb.y = ob[0].y; vb.z = ob[1].x; vb.w = ob[1].y;
             *reinterpret_cast<F4*>(As + lr * CA + seg * 4) = va;
-            *reinterpret_cast<F4*>(Bs + lr * CA + seg * 4) = vb;
+            if (MODE != kFwdLow) *reinterpret_cast<F4*>(Bs + lr * CA + seg * 4) = vb;
         }
     }
     template <class HH = H0>
@@ -418,8 +428,57 @@ struct Fwd2d {
         }
     }
 
+    // NOUT rows x 2 columns of a real image (kFwdRaw / kFwdLow)
+    static DTCWT_D void store_rows(const F2 (&y)[NOUT], float* dst, int64_t rs, int nrow) {
+#pragma unroll
+        for (int i = 0; i < NOUT; ++i)
+            if (i < nrow) *reinterpret_cast<F2*>(dst + (int64_t)i * rs) = y[i];
+    }
+
+    // column pass of the 3-D modes: real images out
+    static DTCWT_D void phase_cols_real(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        const float* As = sm + RX * CX;
+        const float* Bs = As + RX * CA;
+        constexpr int NCP = P * GW / 2;
+        for (int task = tid; task < NCP * (GH / NGV); task += kThreads) {
+            const int strip = task / NCP, cp = task - strip * NCP;
+            const int lrow = Q * NGV * strip;
+            const int orow = P * (GH * by + NGV * strip);
+            const int ocol = P * GW * bx + 2 * cp;
+            const int nrow = (ocol < a.out_cols) ? a.out_rows - orow : 0;
+            float* dst = a.lolo + ((int64_t)bz * a.out_rows + orow) * a.out_cols + ocol;
+            F2 lo[NOUT], hi[NOUT];
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i) { lo[i].x = lo[i].y = 0.f; hi[i].x = hi[i].y = 0.f; }
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                const F2 v = *reinterpret_cast<const F2*>(As + (lrow + j) * CA + 2 * cp);
+                fir_scatter<H0, NGV, HL, TV0>(j, v, a.v0, lo);
+                if (MODE == kFwdRaw) fir_scatter<H1, NGV, HL, TV1>(j, v, a.v1, hi);
+            }
+            store_rows(lo, dst, a.out_cols, nrow);
+            if (MODE == kFwdRaw) {
+                store_rows(hi, dst + a.zs_band, a.out_cols, nrow);
+#pragma unroll
+                for (int i = 0; i < NOUT; ++i) { lo[i].x = lo[i].y = 0.f; hi[i].x = hi[i].y = 0.f; }
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    const F2 v = *reinterpret_cast<const F2*>(Bs + (lrow + j) * CA + 2 * cp);
+                    fir_scatter<H0, NGV, HL, TV0>(j, v, a.v0, lo);
+                    fir_scatter<H1, NGV, HL, TV1>(j, v, a.v1, hi);
+                }
+                store_rows(lo, dst + 2 * a.zs_band, a.out_cols, nrow);
+                store_rows(hi, dst + 3 * a.zs_band, a.out_cols, nrow);
+            }
+        }
+    }
+
     // phase 4: column pass, one task = 2 adjacent columns x NGV groups of rows; results leave from registers
     static DTCWT_D void phase_cols(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        if (MODE != kFwdQ2c) {
+            phase_cols_real(a, sm, bx, by, bz, tid);
+            return;
+        }
         const float* As = sm + RX * CX;
         const float* Bs = As + RX * CA;
         constexpr int NCP = P * GW / 2;                           // column pairs of the tile (CA may be padded)
@@ -495,9 +554,12 @@ struct Inv2dArgs {
 // out = H:g0(y1) + H:g1(y2) reads them back with a register window and stores float4s.
 // No input staging, one block barrier.  Tiles whose halo lies inside the image take a variant compiled
 // without the symmetric-extension logic.
-template <class G0, class G1, int NGV_, int NSTRIP_, int NWIDE_>
+// RAW (3-D transform, y/x passes of one slice, transform3d.py:485-490): the inputs are the four REAL images
+// s0..s3 of Fwd2d's kFwdRaw mode, image s at z + s * zs_band (floats), instead of lowpass + complex sub-bands.
+template <class G0, class G1, int NGV_, int NSTRIP_, int NWIDE_, bool RAW_ = false>
 struct Inv2d {
     typedef Inv2dArgs Args;
+    static constexpr bool RAW = RAW_;
     static constexpr int P = G0::P, Q = G0::Q;
     static constexpr int NGV = NGV_, NSTRIP = NSTRIP_, NWIDE = NWIDE_;
     static constexpr int NGH = 4 / Q;
@@ -580,14 +642,17 @@ struct Inv2d {
         const float* zimg = a.z + (int64_t)bz * a.rows * a.cols + 2 * gj;
         const float* zb = a.yh + 2 * ((int64_t)bz * a.zs_n + gj);
         const float* f[4];
-        if (ROLE == 0) { f[0] = zimg; f[1] = zimg + a.cols; f[2] = zb; f[3] = zb + 2 * 5 * a.zs_band; }
+        if (RAW) {           // role 0: rows of s0 (filtered with g0) and s1 (g1); role 1: s2 and s3
+            const float* sa = zimg + (ROLE == 0 ? 0 : 2) * a.zs_band;
+            f[0] = sa; f[1] = sa + a.cols; f[2] = sa + a.zs_band; f[3] = sa + a.zs_band + a.cols;
+        } else if (ROLE == 0) { f[0] = zimg; f[1] = zimg + a.cols; f[2] = zb; f[3] = zb + 2 * 5 * a.zs_band; }
         else { f[0] = zb + 2 * 2 * a.zs_band; f[1] = zb + 2 * 3 * a.zs_band; f[2] = zb + 2 * 1 * a.zs_band; f[3] = zb + 2 * 4 * a.zs_band; }
         const char* ptr[4];
         int stride[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             ptr[i] = reinterpret_cast<const char*>(f[i]);
-            stride[i] = (ROLE == 0 && i < 2) ? 8 * a.cols : 8 * (int)a.zs_row;      // bytes per quad row (the ABI bounds both)
+            stride[i] = (RAW || (ROLE == 0 && i < 2)) ? 8 * a.cols : 8 * (int)a.zs_row;      // bytes per quad row (the ABI bounds both)
         }
         const float ga0 = a.gain[ROLE == 0 ? 0 : 2], ga1 = a.gain[ROLE == 0 ? 5 : 3];
         const float gb0 = a.gain[1], gb1 = a.gain[4];
@@ -600,7 +665,9 @@ struct Inv2d {
         for (int jq = 0; jq < NQR; ++jq) {
             if (jq + 1 < NQR) load_quad_row<EDGE>(a, ptr, stride, qr0 + jq + 1, nxt);
             F2 at, ab, bt, bb;         // image A (filtered with g0) and image B (g1): top / bottom real rows
-            if (ROLE == 0) {
+            if (RAW) {
+                at = cur.v[0]; ab = cur.v[1]; bt = cur.v[2]; bb = cur.v[3];
+            } else if (ROLE == 0) {
                 at = cur.v[0]; ab = cur.v[1];
                 c2q_rows(cur.v[2], cur.v[3], ga0, ga1, bt, bb);
             } else {

@@ -1,0 +1,239 @@
+// Fused per-level 3-D DT-CWT kernels (float32): the DEPTH pass with the 2x2x2 packers in registers.
+//
+// A 3-D level of the reference (transform3d.py:208-383 forward, :385-526 inverse) filters a volume
+// [D0][D1][D2] along axis 2, 1 and 0 with a (lowpass, highpass) pair and packs seven of the eight
+// octants into 4 complex channels each (cube2c :532-579, c2cube :581-619).  Here a level is two launches:
+//
+//   forward   slices   Fwd2d<..., kFwdRaw>  (fused2d.cuh): axes 2 and 1 of every slice [D1][D2] in one tile kernel,
+//                      four real images s0..s3 per slice  ->  scratch [4][n*D0][D1'][D2']
+//             depth    Z3Fwd (this file): axis 0 of the four scratch volumes, both filters, cube2c in registers
+//                      ->  LLL and the 28 complex channels straight from registers
+//   inverse   depth    Z3Inv: c2cube in registers while the channels are loaded, axis 0 with both filters
+//                      ->  scratch [4][n*D0''][a1][a2]
+//             slices   Inv2d<..., RAW>: axes 1 and 2
+//
+// (The passes commute; only rounding differs from the reference's 2, 1, 0 / 1, 0, 2 order.)
+// Per level every sample is read twice and written twice: 16 B per input voxel instead of the 14 round
+// trips of the one-axis-per-launch composition it replaces.
+//
+// One depth thread owns a 2 x 2 patch of (axis 1, axis 2) -- two rows, one float2 each -- and NG groups
+// along axis 0, so every 2x2x2 octet of the packers lives in its registers.  Lanes run along axis 2
+// (8-byte coalesced loads / stores).  The filter is the same polyphase scatter as the 2-D kernels
+// (fir_scatter, packed FFMA2).  The packers' 1/2 is folded into the taps; the one real output (LLL)
+// and the one real input (Yl) are scaled by 2 instead, which is exact in binary floating point.
+#pragma once
+#include "fused2d.cuh"
+
+namespace dtcwt {
+
+// channel block (4 channels) of the octant with filter types (t0, t1, t2) along axes (0, 1, 2), 1 = highpass:
+// order HLL LHL HHL LLH HLH LHH HHH = (0,1,0) (1,0,0) (1,1,0) (0,0,1) (0,1,1) (1,0,1) (1,1,1)  (transform3d.py:280-288)
+DTCWT_HD constexpr int octant_block(int t0, int t1, int t2) { return t1 + 2 * t0 + 4 * t2 - 1; }
+
+struct Z3Args {
+    const float* s;                 // forward: scratch in; inverse: lowpass Yl [n][a0][a1][a2]
+    float* lll;                     // forward: LLL out [n][L0 * P / Q][h][w]; inverse: scratch out
+    float* yh;                      // complex planar channels (strides below); forward: out, inverse: in
+    int n;
+    int d0, pad0, L0;               // forward: stored slices, replicated slices before them, logical length
+    int h, w;                       // size of one (axis 1, axis 2) image of the depth pass (even)
+    int out_d0, crop0;              // inverse: stored output slices and cropped slices per side (transform3d.py:505-524)
+    int64_t sub_stride, vol_stride; // scratch: floats between the four images s0..s3 / between volumes
+    int64_t zs_n, zs_chan, zs_0, zs_1, zs_2;     // complex strides of yh
+    PhaseTaps lo, hi;               // taps of the pair, times 1/2
+};
+
+// ------------------------------------------------------------------------------- forward depth pass
+template <class FLO, class FHI, int NG_>
+struct Z3Fwd {
+    typedef Z3Args Args;
+    static constexpr int P = FLO::P, Q = FLO::Q, NG = NG_;
+    static constexpr int HL = cmax(spec_lo<FLO>(), spec_lo<FHI>());
+    static constexpr int HR = cmax(spec_hi<FLO>(), spec_hi<FHI>());
+    static constexpr int NR = Q * NG + HL + HR;
+    static constexpr int NOUT = P * NG;
+    static_assert(P == FHI::P && Q == FHI::Q && (NOUT % 2) == 0, "filter pair");
+
+    static DTCWT_HD int64_t groups(const Args& a) { return (a.L0 * P / Q + NOUT - 1) / NOUT; }
+    // gid -> (x pair, y pair, depth group, image s, volume)
+    static DTCWT_HD int64_t total(const Args& a) { return (int64_t)(a.w / 2) * (a.h / 2) * groups(a) * 4 * a.n; }
+
+    static DTCWT_D void run(const Args& a, int64_t gid) {
+        const int wp = a.w / 2, hp = a.h / 2;
+        const int xp = (int)(gid % wp);
+        int64_t r = gid / wp;
+        const int yp = (int)(r % hp);
+        r /= hp;
+        const int64_t ng = groups(a);
+        const int gz = (int)(r % ng);
+        r /= ng;
+        const int sub = (int)(r % 4);
+        const int b = (int)(r / 4);
+        const float* src = a.s + sub * a.sub_stride + b * a.vol_stride + (int64_t)(2 * yp) * a.w + 2 * xp;
+        const int64_t plane = (int64_t)a.h * a.w;
+        F2 lo[2][NOUT], hi[2][NOUT];
+#pragma unroll
+        for (int i = 0; i < NOUT; ++i) { lo[0][i] = zero2(); lo[1][i] = zero2(); hi[0][i] = zero2(); hi[1][i] = zero2(); }
+        const int l0 = Q * NG * gz - HL;
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            const int z = unpad(reflect_any(l0 + j, a.L0), a.pad0, a.d0);
+            const float* p = src + (int64_t)z * plane;
+            const F2 v0 = *reinterpret_cast<const F2*>(p);
+            const F2 v1 = *reinterpret_cast<const F2*>(p + a.w);
+            fir_scatter<FLO, NG, HL>(j, v0, a.lo, lo[0]);
+            fir_scatter<FLO, NG, HL>(j, v1, a.lo, lo[1]);
+            fir_scatter<FHI, NG, HL>(j, v0, a.hi, hi[0]);
+            fir_scatter<FHI, NG, HL>(j, v1, a.hi, hi[1]);
+        }
+        const int t1 = sub & 1, t2 = sub >> 1;                   // filter types of this image along axes 1 and 2
+        const int Lout = a.L0 * P / Q;
+        const int zo = NOUT * gz;                                 // first output slice
+        if (sub == 0) {                                           // LLL: real, undo the folded 1/2
+            float* d = a.lll + ((int64_t)b * Lout + zo) * plane + (int64_t)(2 * yp) * a.w + 2 * xp;
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i) {
+                if (zo + i < Lout) {
+                    F2 u0, u1;
+                    u0.x = 2.f * lo[0][i].x; u0.y = 2.f * lo[0][i].y;
+                    u1.x = 2.f * lo[1][i].x; u1.y = 2.f * lo[1][i].y;
+                    *reinterpret_cast<F2*>(d + (int64_t)i * plane) = u0;
+                    *reinterpret_cast<F2*>(d + (int64_t)i * plane + a.w) = u1;
+                }
+            }
+        } else {
+            pack(a, lo, octant_block(0, t1, t2), b, zo, yp, xp, Lout);
+        }
+        pack(a, hi, octant_block(1, t1, t2), b, zo, yp, xp, Lout);
+    }
+
+    // cube2c (transform3d.py:532-579; the 1/2 is in the taps): octet corners by (axis 0, axis 1, axis 2) parity
+    //   A=(0,0,0) B=(0,1,0) C=(1,0,0) D=(1,1,0) E=(0,0,1) F=(0,1,1) G=(1,0,1) H=(1,1,1)
+    static DTCWT_D void pack(const Args& a, const F2 (&y)[2][NOUT], int block, int b, int zo, int yp, int xp, int Lout) {
+        float* z = a.yh + 2 * ((int64_t)b * a.zs_n + (int64_t)(4 * block) * a.zs_chan + (int64_t)(zo / 2) * a.zs_0 +
+                               (int64_t)yp * a.zs_1 + (int64_t)xp * a.zs_2);
+        const int64_t cs = 2 * a.zs_chan;
+#pragma unroll
+        for (int q = 0; q < NOUT / 2; ++q) {
+            if (zo + 2 * q < Lout) {
+                const float A = y[0][2 * q].x, E = y[0][2 * q].y, B = y[1][2 * q].x, F = y[1][2 * q].y;
+                const float C = y[0][2 * q + 1].x, G = y[0][2 * q + 1].y, D = y[1][2 * q + 1].x, H = y[1][2 * q + 1].y;
+                float* zz = z + 2 * (int64_t)q * a.zs_0;
+                F2 c;
+                c.x = A - G - D - F; c.y = B - H + C + E;
+                *reinterpret_cast<F2*>(zz) = c;                                   // p
+                c.x = A - G + D + F; c.y = -B + H + C + E;
+                *reinterpret_cast<F2*>(zz + cs) = c;                              // q
+                c.x = A + G + D - F; c.y = B + H - C + E;
+                *reinterpret_cast<F2*>(zz + 2 * cs) = c;                          // r
+                c.x = A + G - D + F; c.y = -B - H - C + E;
+                *reinterpret_cast<F2*>(zz + 3 * cs) = c;                          // s
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------- inverse depth pass
+// scratch image s (axis-1 type s & 1, axis-2 type s >> 1) = G0 along axis 0 of the lowpass-in-depth octant
+//                                                          + G1 along axis 0 of the highpass-in-depth octant
+template <class GLO, class GHI, int NG_>
+struct Z3Inv {
+    typedef Z3Args Args;
+    static constexpr int P = GLO::P, Q = GLO::Q, NG = NG_;
+    static constexpr int HL = round_up(cmax(spec_lo<GLO>(), spec_lo<GHI>()), 2);     // whole octets
+    static constexpr int HR = round_up(cmax(spec_hi<GLO>(), spec_hi<GHI>()), 2);
+    static constexpr int NR = Q * NG + HL + HR;
+    static constexpr int NOUT = P * NG;
+    static_assert(P == GHI::P && Q == GHI::Q && ((Q * NG) % 2) == 0, "filter pair");
+
+    // d0 = slices of the lowpass / real octants (even)
+    static DTCWT_HD int64_t groups(const Args& a) { return (a.d0 + Q * NG - 1) / (Q * NG); }
+    static DTCWT_HD int64_t total(const Args& a) { return (int64_t)(a.w / 2) * (a.h / 2) * groups(a) * 4 * a.n; }
+
+    struct Oct { F2 v[2][2]; };      // [axis-0 parity][axis-1 parity], .x / .y = axis-2 parity
+
+    // c2cube (transform3d.py:581-619; the 1/2 is in the taps)
+    static DTCWT_D void unpack(const Args& a, int block, int b, int oz, int yp, int xp, Oct& o) {
+        const float* z = a.yh + 2 * ((int64_t)b * a.zs_n + (int64_t)(4 * block) * a.zs_chan + (int64_t)oz * a.zs_0 +
+                                     (int64_t)yp * a.zs_1 + (int64_t)xp * a.zs_2);
+        const int64_t cs = 2 * a.zs_chan;
+        const F2 p = *reinterpret_cast<const F2*>(z), q = *reinterpret_cast<const F2*>(z + cs);
+        const F2 r = *reinterpret_cast<const F2*>(z + 2 * cs), s = *reinterpret_cast<const F2*>(z + 3 * cs);
+        o.v[0][0].x = p.x + q.x + r.x + s.x;        // A
+        o.v[0][0].y = p.y + q.y + r.y + s.y;        // E
+        o.v[0][1].x = p.y - q.y + r.y - s.y;        // B
+        o.v[0][1].y = -p.x + q.x - r.x + s.x;       // F
+        o.v[1][0].x = p.y + q.y - r.y - s.y;        // C
+        o.v[1][0].y = -p.x - q.x + r.x + s.x;       // G
+        o.v[1][1].x = -p.x + q.x + r.x - s.x;       // D
+        o.v[1][1].y = -p.y + q.y + r.y - s.y;       // H
+    }
+
+    static DTCWT_D void run(const Args& a, int64_t gid) {
+        const int wp = a.w / 2, hp = a.h / 2;
+        const int xp = (int)(gid % wp);
+        int64_t r = gid / wp;
+        const int yp = (int)(r % hp);
+        r /= hp;
+        const int64_t ng = groups(a);
+        const int gz = (int)(r % ng);
+        r /= ng;
+        const int sub = (int)(r % 4);
+        const int b = (int)(r / 4);
+        const int t1 = sub & 1, t2 = sub >> 1;
+        const int64_t plane = (int64_t)a.h * a.w;
+        const int noct = a.d0 / 2;
+        F2 acc[2][NOUT];
+#pragma unroll
+        for (int i = 0; i < NOUT; ++i) { acc[0][i] = zero2(); acc[1][i] = zero2(); }
+        const int o0 = (Q * NG * gz - HL) / 2;                   // first octet along axis 0 (may be negative)
+#pragma unroll
+        for (int jq = 0; jq < NR / 2; ++jq) {
+            // symmetric extension at octet granularity: a mirrored octet has its axis-0 parities exchanged
+            int oz = o0 + jq;
+            bool flip = false;
+            if (oz < 0) { oz = -1 - oz; flip = true; } else if (oz >= noct) { oz = 2 * noct - 1 - oz; flip = true; }
+            oz = oz < 0 ? 0 : (oz >= noct ? noct - 1 : oz);     // further out only feeds outputs that are never stored
+            Oct lo, hi;
+            if (sub == 0) {
+                const float* p = a.s + ((int64_t)b * a.d0 + 2 * oz) * plane + (int64_t)(2 * yp) * a.w + 2 * xp;
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+#pragma unroll
+                    for (int f = 0; f < 2; ++f) {
+                        const F2 v = *reinterpret_cast<const F2*>(p + (int64_t)e * plane + (int64_t)f * a.w);
+                        lo.v[e][f].x = 2.f * v.x; lo.v[e][f].y = 2.f * v.y;
+                    }
+            } else {
+                unpack(a, octant_block(0, t1, t2), b, oz, yp, xp, lo);
+            }
+            unpack(a, octant_block(1, t1, t2), b, oz, yp, xp, hi);
+            if (flip) {                                          // selects, not indexed: the octets stay in registers
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+                    F2 t = lo.v[0][f]; lo.v[0][f] = lo.v[1][f]; lo.v[1][f] = t;
+                    t = hi.v[0][f]; hi.v[0][f] = hi.v[1][f]; hi.v[1][f] = t;
+                }
+            }
+            fir_scatter<GLO, NG, HL>(2 * jq, lo.v[0][0], a.lo, acc[0]);
+            fir_scatter<GLO, NG, HL>(2 * jq, lo.v[0][1], a.lo, acc[1]);
+            fir_scatter<GHI, NG, HL>(2 * jq, hi.v[0][0], a.hi, acc[0]);
+            fir_scatter<GHI, NG, HL>(2 * jq, hi.v[0][1], a.hi, acc[1]);
+            fir_scatter<GLO, NG, HL>(2 * jq + 1, lo.v[1][0], a.lo, acc[0]);
+            fir_scatter<GLO, NG, HL>(2 * jq + 1, lo.v[1][1], a.lo, acc[1]);
+            fir_scatter<GHI, NG, HL>(2 * jq + 1, hi.v[1][0], a.hi, acc[0]);
+            fir_scatter<GHI, NG, HL>(2 * jq + 1, hi.v[1][1], a.hi, acc[1]);
+        }
+        float* d = a.lll + sub * a.sub_stride + b * a.vol_stride + (int64_t)(2 * yp) * a.w + 2 * xp;
+#pragma unroll
+        for (int i = 0; i < NOUT; ++i) {
+            const int zo = NOUT * gz + i - a.crop0;
+            if (zo >= 0 && zo < a.out_d0) {
+                *reinterpret_cast<F2*>(d + (int64_t)zo * plane) = acc[0][i];
+                *reinterpret_cast<F2*>(d + (int64_t)zo * plane + a.w) = acc[1][i];
+            }
+        }
+    }
+};
+
+}  // namespace dtcwt

@@ -115,10 +115,18 @@ class Transform3d(object):
                 if t["h0o"].shape[0] % 2 == 0 or t["h1o"].shape[0] % 2 == 0:
                     raise ValueError("even-length biorthogonal filters are not supported by the 3-D transform yet")
                 if discard_level_1:
-                    for ax in (3, 2, 1):     # reference _level1_xfm_no_highpass :291-315
-                        Yl = _ops.colfilter(Yl, t["h0o"], ax)
+                    fused = _ops.lowpass3d(Yl, t["h0o"])
+                    if fused is not None:
+                        Yl = fused
+                    else:
+                        for ax in (3, 2, 1):     # reference _level1_xfm_no_highpass :291-315
+                            Yl = _ops.colfilter(Yl, t["h0o"], ax)
                 else:
-                    Yl, Yh[0] = self._split(Yl, lambda A, ax, hi: _ops.colfilter(A, t["h1o"] if hi else t["h0o"], ax))
+                    fused = _ops.fwd3d_level1(Yl, t["h0o"], t["h1o"])
+                    if fused is not None:
+                        Yl, Yh[0] = fused
+                    else:
+                        Yl, Yh[0] = self._split(Yl, lambda A, ax, hi: _ops.colfilter(A, t["h1o"] if hi else t["h0o"], ax))
             else:
                 n = 1 if self.ext_mode == 4 else 2
                 pads = {ax: ((n, n) if int(Yl.shape[ax]) % (4 * n) else (0, 0)) for ax in (1, 2, 3)}
@@ -128,7 +136,11 @@ class Transform3d(object):
                         return _ops.coldfilt(A, t["h1b"], t["h1a"], ax, pads[ax])
                     return _ops.coldfilt(A, t["h0b"], t["h0a"], ax, pads[ax])
 
-                Yl, Yh[lev] = self._split(Yl, dfilt)
+                fused = _ops.fwd3d_levelq(Yl, t["h0b"], t["h0a"], t["h1b"], t["h1a"], [pads[ax][0] for ax in (1, 2, 3)])
+                if fused is not None:
+                    Yl, Yh[lev] = fused
+                else:
+                    Yl, Yh[lev] = self._split(Yl, dfilt)
             Ysc[lev] = Yl
         views = tuple(None if h is None else h.permute(0, 2, 3, 4, 1) for h in Yh)
         return Pyramid(Yl, views, tuple(Ysc)) if include_scale else Pyramid(Yl, views)
@@ -156,10 +168,18 @@ class Transform3d(object):
         L = len(Yh)
         for lev in range(L - 1, -1, -1):
             if lev == 0:
+                fused = None
                 if Yh[0] is None:
-                    for ax in (2, 1, 3):     # reference _level1_ifm_no_highpass :442-456, axes 1, 0, 2
-                        Yl = _ops.colfilter(Yl, t["g0o"], ax)
+                    fused = _ops.lowpass3d(Yl, t["g0o"], inverse=True)
+                    if fused is None:
+                        for ax in (2, 1, 3):     # reference _level1_ifm_no_highpass :442-456, axes 1, 0, 2
+                            Yl = _ops.colfilter(Yl, t["g0o"], ax)
                 else:
+                    self._check_sizes(Yl, Yh[0])
+                    fused = _ops.inv3d_level1(Yl, Yh[0], t["g0o"], t["g1o"])
+                if fused is not None:
+                    Yl = fused
+                elif Yh[0] is not None:
                     Yl = self._merge(Yl, Yh[0], lambda A, ax, hi, out: _ops.colfilter(
                         A, t["g1o"] if hi else t["g0o"], ax, out=out, accumulate=out is not None))
             else:
@@ -172,14 +192,20 @@ class Transform3d(object):
                     ha, hb = (t["g1b"], t["g1a"]) if hi else (t["g0b"], t["g0a"])
                     return _ops.colifilt(A, ha, hb, ax, crops[ax], out=out, accumulate=out is not None)
 
-                Yl = self._merge(Yl, Yh[lev], ifilt)
+                self._check_sizes(Yl, Yh[lev])
+                fused = _ops.inv3d_levelq(Yl, Yh[lev], t["g0b"], t["g0a"], t["g1b"], t["g1a"], [crops[ax] for ax in (1, 2, 3)])
+                Yl = fused if fused is not None else self._merge(Yl, Yh[lev], ifilt)
         return Yl
+
+    @staticmethod
+    def _check_sizes(Yl, yh):
+        if tuple(Yl.shape[1:]) != tuple(2 * int(s) for s in yh.shape[2:]) or Yl.shape[0] != yh.shape[0]:
+            raise ValueError("lowpass and highpass sizes are not valid for the inverse 3-D transform")
 
     @staticmethod
     def _merge(Yl, yh, filt):
         """One synthesis level: merge lo/hi pairs along axis 1, then 0, then 2 (tensor axes 2, 1, 3)."""
-        if tuple(Yl.shape[1:]) != tuple(2 * int(s) for s in yh.shape[2:]) or Yl.shape[0] != yh.shape[0]:
-            raise ValueError("lowpass and highpass sizes are not valid for the inverse 3-D transform")
+        Transform3d._check_sizes(Yl, yh)
         parts = {(0, 0, 0): Yl}
         for i, o in enumerate(_OCTANTS):
             parts[o] = _ops.c2cube(yh, 4 * i)

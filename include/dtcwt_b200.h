@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define DTCWT_B200_VERSION 100          /* 0.1.0 */
+#define DTCWT_B200_VERSION 200          /* 0.2.0: + fused 3-D levels */
 #define DTCWT_B200_MAX_TAPS 32          /* longest filter accepted (qshift_32) */
 
 #define DTCWT_B200_OK 0
@@ -177,6 +177,51 @@ int dtcwt_b200_inv2d_levelq_f32(const float *z, const float *yh, float *out, int
 int dtcwt_b200_inv2d_level1_f32(const float *z, const float *yh, float *out, int64_t n, int64_t rows, int64_t cols,
                                 const double *g0o, int m0, const double *g1o, int m1, const double *gain,
                                 int64_t zs_n, int64_t zs_band, int64_t zs_row, void *stream);
+
+/* ---- fused per-level 3-D transform (float32) -----------------------------------
+ * A level of Transform3d is two launches: the two in-slice axes of every slice in one
+ * tile kernel (the 2-D kernels above in a mode that keeps the four real images), and
+ * the depth axis with the 2x2x2 packers cube2c / c2cube in registers.  Volumes are
+ * C-contiguous [n][d0][d1][d2]; yh is the planar complex array of the level, element
+ * (b, chan, i, j, k) at yh + 2*(b*zs_n + chan*zs_chan + i*zs_0 + j*zs_1 + k*zs_2), the
+ * 28 channels in the reference's order (transform3d.py:280-288).  `scratch` is caller-
+ * owned device memory of the stated size (the library never allocates).
+ *
+ *   fwd3d_level1_lo  replaces _level1_xfm_no_highpass  (numpy/transform3d.py:291-315)
+ *   inv3d_level1_lo  replaces _level1_ifm_no_highpass  (:442-456)
+ *                    y = colfilter(h) along all three axes; scratch n*d0*d1*d2 floats
+ *   fwd3d_level1     replaces _level1_xfm (:208-289), odd-length taps; lll [n][d0][d1][d2],
+ *                    yh [n][28][d0/2][d1/2][d2/2]; scratch 4*n*d0*d1*d2 floats
+ *   inv3d_level1     replaces _level1_ifm (:385-440), odd-length taps; scratch 4*n*a0*a1*a2
+ *   fwd3d_levelq     replaces _level2_xfm (:317-383); pad_i = replicated samples attached to
+ *                    EACH side of axis i (ext_mode 4: 0 or 1, ext_mode 8: 0 or 2; :322-335);
+ *                    with L_i = d_i + 2 pad_i: lll [n][L0/2][L1/2][L2/2], yh [n][28][L0/4][L1/4][L2/4];
+ *                    scratch n*d0*L1*L2 floats
+ *   inv3d_levelq     replaces _level2_ifm (:458-526); yl [n][a0][a1][a2]; crop_i = samples
+ *                    dropped at EACH end of axis i (:505-524); out [n][2a0-2crop0][2a1-2crop1]
+ *                    [2a2-2crop2]; scratch 4*n*(2a0-2crop0)*a1*a2 floats
+ * (lo_a, lo_b), (hi_a, hi_b) as for the 2-D levels.  EUNSUPPORTED: in-slice sides < 32,
+ * depth < 16, pointers not 16-byte aligned, tap counts / correlations as for the 2-D levels;
+ * callers then compose the level from the per-axis primitives.
+ */
+int dtcwt_b200_fwd3d_level1_lo_f32(const float *x, float *y, float *scratch, int64_t n, int64_t d0, int64_t d1,
+                                   int64_t d2, const double *h0o, int m0, void *stream);
+int dtcwt_b200_inv3d_level1_lo_f32(const float *yl, float *out, float *scratch, int64_t n, int64_t d0, int64_t d1,
+                                   int64_t d2, const double *g0o, int m0, void *stream);
+int dtcwt_b200_fwd3d_level1_f32(const float *x, float *lll, float *yh, float *scratch, int64_t n, int64_t d0,
+                                int64_t d1, int64_t d2, const double *h0o, int m0, const double *h1o, int m1,
+                                int64_t zs_n, int64_t zs_chan, int64_t zs_0, int64_t zs_1, int64_t zs_2, void *stream);
+int dtcwt_b200_inv3d_level1_f32(const float *yl, const float *yh, float *out, float *scratch, int64_t n, int64_t a0,
+                                int64_t a1, int64_t a2, const double *g0o, int m0, const double *g1o, int m1,
+                                int64_t zs_n, int64_t zs_chan, int64_t zs_0, int64_t zs_1, int64_t zs_2, void *stream);
+int dtcwt_b200_fwd3d_levelq_f32(const float *x, float *lll, float *yh, float *scratch, int64_t n, int64_t d0,
+                                int64_t d1, int64_t d2, int pad0, int pad1, int pad2, const double *lo_a,
+                                const double *lo_b, const double *hi_a, const double *hi_b, int m, int64_t zs_n,
+                                int64_t zs_chan, int64_t zs_0, int64_t zs_1, int64_t zs_2, void *stream);
+int dtcwt_b200_inv3d_levelq_f32(const float *yl, const float *yh, float *out, float *scratch, int64_t n, int64_t a0,
+                                int64_t a1, int64_t a2, int crop0, int crop1, int crop2, const double *lo_a,
+                                const double *lo_b, const double *hi_a, const double *hi_b, int m, int64_t zs_n,
+                                int64_t zs_chan, int64_t zs_0, int64_t zs_1, int64_t zs_2, void *stream);
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,7 @@
 #include "../../dtcwt_b200/csrc/generic_kernels.cuh"
 #include "../../dtcwt_b200/csrc/fused2d.cuh"
 #include "../../dtcwt_b200/csrc/stream2d.cuh"
+#include "../../dtcwt_b200/csrc/fused3d.cuh"
 #include "../../dtcwt_b200/csrc/axis_pass.cuh"
 
 namespace dtcwt {
@@ -33,6 +34,13 @@ template <class K>
 static int launch_axis(const AxisArgs& a, void* /*stream*/) {
     const int64_t total = K::total(a);
     for (int64_t gid = total - 1; gid >= 0; --gid) K::run(a, gid);     // descending: exposes writes outside a thread's outputs
+    return DTCWT_B200_OK;
+}
+
+template <class K>
+static int launch_z3(const Z3Args& a, void* /*stream*/) {
+    const int64_t total = K::total(a);
+    for (int64_t gid = total - 1; gid >= 0; --gid) K::run(a, gid);
     return DTCWT_B200_OK;
 }
 
@@ -119,6 +127,7 @@ static int launch_fwds1(typename K::Args& a, void* /*stream*/) {
 #include "../../dtcwt_b200/csrc/abi_generic.inl"
 #include "../../dtcwt_b200/csrc/abi_fused2d.inl"
 #include "../../dtcwt_b200/csrc/abi_axis.inl"
+#include "../../dtcwt_b200/csrc/abi_fused3d.inl"
 
 extern "C" {
 

@@ -32,7 +32,7 @@ def test_library_exports_every_symbol():
     for sym in declared_symbols():
         assert hasattr(handle, sym), sym
     handle.dtcwt_b200_version.restype = ctypes.c_int
-    assert handle.dtcwt_b200_version() == 100
+    assert handle.dtcwt_b200_version() == _lib.ABI_VERSION
     assert handle.dtcwt_b200_is_device_build() == 1
     handle.dtcwt_b200_error_string.restype = ctypes.c_char_p
     assert b"invalid" in handle.dtcwt_b200_error_string(-1)

@@ -390,3 +390,73 @@ def test_pyramid_numpy_edits_reach_inverse(backend, monkeypatch):
     q = xf.forward(X, nlevels=2)
     q.lowpass                                      # reading alone must not change anything
     assert np.abs(xf.inverse(q).cpu().numpy() - X).max() < 1e-5
+
+
+# ----------------------------------------------------------------------------- fused 3-D levels (fused3d.cuh)
+def _launched(fn):
+    """Run fn() and return (result, set of C-ABI symbols it launched)."""
+    from dtcwt_b200 import _lib
+    seen = []
+
+    def hook(symbol, thunk):
+        seen.append(symbol)
+        thunk()
+
+    _lib.set_launch_hook(hook)
+    try:
+        out = fn()
+    finally:
+        _lib.set_launch_hook(None)
+    return out, set(seen)
+
+
+@pytest.mark.parametrize("shape,em,disc,names", [
+    ((32, 40, 48), 4, True, ("near_sym_b", "qshift_b")),       # config-4 shape family: level 1 lowpass only
+    ((32, 40, 48), 4, False, ("near_sym_b", "qshift_b")),      # full level 1 (28 channels at n/2)
+    ((38, 42, 34), 4, False, ("near_sym_a", "qshift_a")),      # level 2 input not a multiple of 4: pad 1 / crop 1 on every axis
+    ((40, 36, 44), 8, True, ("antonini", "qshift_06")),        # ext_mode 8: pad 2 / crop 2 (transform3d.py:329-335, 515-524)
+    ((32, 64, 32), 4, True, ("legall", "qshift_d")),           # 18-tap q-shift pair
+])
+def test_fused3d_levels_vs_oracle(backend, shape, em, disc, names):
+    """The fused 3-D level kernels (slices + depth pass, packers in registers) against the CPU oracle, and the launch
+    record shows that the fused entry points -- not the per-axis composition -- produced the result."""
+    rs = np.random.RandomState(12)
+    X = rs.rand(2, *shape).astype(np.float32)
+    xf = dtcwt_b200.Transform3d(*names, ext_mode=em)
+    p, fwd_syms = _launched(lambda: xf.forward_channels(X, 2, discard_level_1=disc))
+    Z, inv_syms = _launched(lambda: xf.inverse(p))
+    assert "dtcwt_b200_fwd3d_levelq_f32" in fwd_syms and "dtcwt_b200_inv3d_levelq_f32" in inv_syms
+    assert ("dtcwt_b200_fwd3d_level1_lo_f32" if disc else "dtcwt_b200_fwd3d_level1_f32") in fwd_syms
+    assert ("dtcwt_b200_inv3d_level1_lo_f32" if disc else "dtcwt_b200_inv3d_level1_f32") in inv_syms
+    assert not any(s.startswith(("dtcwt_b200_col", "dtcwt_b200_cube2c", "dtcwt_b200_c2cube")) for s in fwd_syms | inv_syms)
+    to = O.Transform3d(coeffs.biort(names[0]), coeffs.qshift(names[1]), ext_mode=em)
+    for i in range(2):
+        po = to.forward(X[i], 2, discard_level_1=disc)
+        assert rel_err(p.lowpass[i], po.lowpass) < REL_TOL
+        for l in range(2):
+            if po.highpasses[l] is None:
+                assert p.highpasses[l] is None
+            else:
+                assert p.highpasses[l][i].shape == po.highpasses[l].shape
+                assert rel_err(p.highpasses[l][i], po.highpasses[l]) < REL_TOL
+        assert rel_err(npy(Z)[i], to.inverse(po)) < 2 * REL_TOL
+    if not disc:
+        assert np.abs(npy(Z) - X).max() < 1e-5
+
+
+def test_fused3d_equals_per_axis_composition(backend):
+    from dtcwt_b200 import _ops
+    X = np.random.RandomState(13).rand(1, 32, 32, 64).astype(np.float32)
+    xf = dtcwt_b200.Transform3d("near_sym_b", "qshift_b")
+    p = xf.forward_channels(X, 2)
+    Z = npy(xf.inverse(p))
+    _ops.FUSED_ENABLED = False
+    try:
+        q = xf.forward_channels(X, 2)
+        Zq = npy(xf.inverse(q))
+    finally:
+        _ops.FUSED_ENABLED = True
+    assert rel_err(p.lowpass, q.lowpass) < REL_TOL
+    for a, b in zip(p.highpasses, q.highpasses):
+        assert rel_err(a, b) < REL_TOL
+    assert rel_err(Z, Zq) < REL_TOL
