@@ -19,11 +19,11 @@ from .transform1d import Transform1d
 from .transform2d import Transform2d
 from .transform3d import Transform3d
 from .backend import register, BACKEND_NAME
-from . import coeffs, lowlevel
+from . import coeffs, lowlevel, registration, sampling
 from .coeffs import biort, qshift
 from .lowlevel import colfilter, coldfilt, colifilt
 
 __version__ = "0.1.0"
 
 __all__ = ["Pyramid", "Transform1d", "Transform2d", "Transform3d", "register", "BACKEND_NAME",
-           "coeffs", "lowlevel", "biort", "qshift", "colfilter", "coldfilt", "colifilt"]
+           "coeffs", "lowlevel", "registration", "sampling", "biort", "qshift", "colfilter", "coldfilt", "colifilt"]

@@ -31,6 +31,13 @@ _TYPED = {
     "unpack1d": [_P, _P, _L, _L, _L, _D, _P],
     "cube2c": [_P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _P],
     "c2cube": [_P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _P],
+    "reg_qtilde": [_P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _P],
+    "sample": [_P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _I, _TAPS, _TAPS, _P],
+}
+_UNTYPED = {
+    "reg_boxrescale": [_P, _P, _L, _L, _L, _L, _L, _I, _P],
+    "reg_solve": [_P, _P, _L, _I, _P],
+    "reg_coords": [_P, _P, _P, _L, _L, _L, _L, _L, _I, _P],
 }
 _F32_ONLY = {
     "fwd2d_level1": [_P, _P, _P, _L, _L, _L, _I, _I, _TAPS, _I, _TAPS, _I, _L, _L, _L, _P],
@@ -47,7 +54,7 @@ _F32_ONLY = {
 
 EXPORTS = (["dtcwt_b200_version", "dtcwt_b200_error_string", "dtcwt_b200_is_device_build"]
            + ["dtcwt_b200_%s_%s" % (n, s) for n in _TYPED for s in ("f32", "f64")]
-           + ["dtcwt_b200_%s_f32" % n for n in _F32_ONLY])
+           + ["dtcwt_b200_%s_f32" % n for n in _F32_ONLY] + ["dtcwt_b200_%s" % n for n in _UNTYPED])
 
 
 def _bind(path, check_version=True):
@@ -68,6 +75,10 @@ def _bind(path, check_version=True):
             fn.argtypes = args
     for name, args in _F32_ONLY.items():
         fn = getattr(lib, "dtcwt_b200_%s_f32" % name)
+        fn.restype = c_int
+        fn.argtypes = args
+    for name, args in _UNTYPED.items():
+        fn = getattr(lib, "dtcwt_b200_%s" % name)
         fn.restype = c_int
         fn.argtypes = args
     return lib
@@ -130,7 +141,7 @@ def call_optional(name, dtype_suffix, *args):
 
 
 def call(name, dtype_suffix, *args):
-    symbol = "dtcwt_b200_%s_%s" % (name, dtype_suffix)
+    symbol = "dtcwt_b200_%s_%s" % (name, dtype_suffix) if dtype_suffix else "dtcwt_b200_%s" % name
     fn = getattr(lib(), symbol)
     if _LAUNCH_HOOK is None:
         check(fn(*args))

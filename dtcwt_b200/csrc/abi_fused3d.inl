@@ -200,6 +200,7 @@ int dtcwt_b200_fwd3d_levelq_f32(const float* x, float* lll, float* yh, float* sc
     taps_dec(z.lo, lo_a, lo_b, m, true, 0.5);
     taps_dec(z.hi, hi_a, hi_b, m, false, 0.5);
     if (m == 10) return launch_z3<Z3FwdQ<10>::type>(z, stream);
+    if (m == 14 && env_int("DTCWT_B200_Z3_NG", 4) == 2) return launch_z3<Z3Fwd<SpecDec<14, true>, SpecDec<14, false>, 2> >(z, stream);
     if (m == 14) return launch_z3<Z3FwdQ<14>::type>(z, stream);
     return launch_z3<Z3FwdQ<18>::type>(z, stream);
 }
@@ -231,6 +232,7 @@ int dtcwt_b200_inv3d_levelq_f32(const float* yl, const float* yh, float* out, fl
     taps_int(z.lo, lo_a, lo_b, m, true, 0.5);
     taps_int(z.hi, hi_a, hi_b, m, false, 0.5);
     if (m == 10) rc = launch_z3<Z3InvQ<10>::type>(z, stream);
+    else if (m == 14 && env_int("DTCWT_B200_Z3_NG", 4) == 2) rc = launch_z3<Z3Inv<SpecInt<14, true>, SpecInt<14, false>, 2> >(z, stream);
     else if (m == 14) rc = launch_z3<Z3InvQ<14>::type>(z, stream);
     else rc = launch_z3<Z3InvQ<18>::type>(z, stream);
     if (rc) return rc;

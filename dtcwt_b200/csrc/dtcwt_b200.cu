@@ -5,6 +5,7 @@
 #include "generic_kernels.cuh"
 #include "fused2d.cuh"
 #include "fused3d.cuh"
+#include "registration.cuh"
 #include "axis_pass.cuh"
 
 namespace dtcwt {
@@ -64,6 +65,7 @@ static int launch_z3(const Z3Args& a, void* stream) {
 }  // namespace dtcwt
 
 #include "abi_generic.inl"
+#include "abi_reg.inl"
 #include "fused2d_launch.cuh"
 #include "abi_fused2d.inl"
 #include "abi_axis.inl"

@@ -274,22 +274,40 @@ struct Fwd2d {
     }
 
     // phase 1 / 2: symmetric extension (utils.py:136-153) of tiles on the image border, inside smem
+    // Only the rows / columns of the tile that lie OUTSIDE the stored array are visited (the first n_lo and the ones from
+    // hi0 on): on the small slices of a 3-D volume every tile touches a border, and a sweep over the whole tile cost
+    // more than the filtering itself.  Sources are stored samples, which no patch writes, so there is no ordering hazard.
+    static DTCWT_HD void outside_range(int L0, int extent, int pad_lo, int len, int& n_lo, int& hi0) {
+        n_lo = pad_lo - L0;
+        n_lo = n_lo < 0 ? 0 : (n_lo > extent ? extent : n_lo);
+        hi0 = pad_lo + len - L0;
+        hi0 = hi0 < n_lo ? n_lo : (hi0 > extent ? extent : hi0);
+    }
     static DTCWT_D void phase_patch_rows(const Args& a, float* sm, int bx, int by, int bz, int tid) {
         const int L0 = row0(by);
         if (!touches_edge(L0, RX, a.pr_lo, a.rows)) return;
-        for (int e = tid; e < RX * CX; e += kThreads) {
-            const int lr = e / CX, lc = e - lr * CX;
+        int n_lo, hi0;
+        outside_range(L0, RX, a.pr_lo, a.rows, n_lo, hi0);
+        const int n_out = n_lo + (RX - hi0);
+        for (int e = tid; e < n_out * CX; e += kThreads) {
+            const int k = e / CX, lc = e - k * CX;
+            const int lr = k < n_lo ? k : hi0 + (k - n_lo);
             const int src = mirror_src(L0 + lr, a.Lr, a.pr_lo, a.rows, L0, RX);
-            if (src >= 0) sm[e] = sm[src * CX + lc];
+            if (src >= 0) sm[lr * CX + lc] = sm[src * CX + lc];
         }
     }
     static DTCWT_D void phase_patch_cols(const Args& a, float* sm, int bx, int by, int bz, int tid) {
         const int L0 = col0(bx);
         if (!touches_edge(L0, CX, a.pc_lo, a.cols)) return;
-        for (int e = tid; e < RX * CX; e += kThreads) {
-            const int lr = e / CX, lc = e - lr * CX;
+        int n_lo, hi0;
+        outside_range(L0, CX, a.pc_lo, a.cols, n_lo, hi0);
+        const int n_out = n_lo + (CX - hi0);
+        if (n_out == 0) return;
+        for (int e = tid; e < RX * n_out; e += kThreads) {
+            const int lr = e / n_out, k = e - lr * n_out;
+            const int lc = k < n_lo ? k : hi0 + (k - n_lo);
             const int src = mirror_src(L0 + lc, a.Lc, a.pc_lo, a.cols, L0, CX);
-            if (src >= 0) sm[e] = sm[lr * CX + src];
+            if (src >= 0) sm[lr * CX + lc] = sm[lr * CX + src];
         }
     }
 

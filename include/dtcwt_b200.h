@@ -223,6 +223,47 @@ int dtcwt_b200_inv3d_levelq_f32(const float *yl, const float *yh, float *out, fl
                                 const double *lo_b, const double *hi_a, const double *hi_b, int m, int64_t zs_n,
                                 int64_t zs_chan, int64_t zs_0, int64_t zs_1, int64_t zs_2, void *stream);
 
+/* ---- registration and re-sampling (float64 arithmetic) ------------------------------
+ * replaces dtcwt/registration.py (estimatereg :304-372 and its helpers) and dtcwt/sampling.py
+ * (sample :105, rescale :131, sample_highpass :192, rescale_highpass :224).
+ *
+ *   reg_qtilde     qtildematrices (:141-212) for ONE level, with confidence (:84-139) and phasegradient
+ *                  (:32-76) inside: src / ref are the level's six complex sub-bands of the (warped) source
+ *                  and of the reference image, element (b, band, i, j) at 2*(b*x_n + band*x_band + i*x_row
+ *                  + j*x_col).  reduce == 0: qt is [n][h][w][27] float64; reduce != 0: qt is [n][27], the
+ *                  sum over the image ADDED to its content (the global estimate, :333-338).
+ *   reg_boxrescale out (+)= rescale(_boxfilter(qt, 3), (H, W), 'bilinear')  (:357-362, :425-446)
+ *   reg_solve      solvetransform (:214-257): avecs[i] (+)= solve(Q_i, -q_i), Q_i holding ONLY the upper
+ *                  triangle of the 27-vector's 21 matrix elements, as the reference does (:229-232)
+ *   reg_coords     avecs [n][H][W][6] -> xs, ys [n][h][w]; mode 0: velocityfield(avecs, (h, w), 'bilinear')
+ *                  (:374-393), mode 1: the pixel coordinates warp / warphighpass sample at (:395-423)
+ *   sample         im element (b, y, x, c) at k*(b*i_n + y*i_y + x*i_x + c*i_c), out likewise with o_*;
+ *                  k = 2 for complex (interleaved).  method 0 nearest / 1 bilinear / 2 lanczos / 3 the
+ *                  7-tap lanczos of upsample() (sampling.py:312-320; doubled rescale grid only).  coords 0:
+ *                  positions from xs / ys ([oh][ow] planes, coord_n elements apart per batch item, 0 =
+ *                  shared); coords 1: the rescale grid.  wx / wy non-NULL (HOST arrays, C <= 8): complex
+ *                  sub-bands, phase un-rolled by exp(-j(wx x + wy y)) before sampling and re-rolled after.
+ */
+int dtcwt_b200_reg_qtilde_f32(const float *src, const float *ref, double *qt, int64_t n, int64_t h, int64_t w,
+                              int64_t s_n, int64_t s_band, int64_t s_row, int64_t s_col, int64_t r_n,
+                              int64_t r_band, int64_t r_row, int64_t r_col, int reduce, void *stream);
+int dtcwt_b200_reg_qtilde_f64(const double *src, const double *ref, double *qt, int64_t n, int64_t h, int64_t w,
+                              int64_t s_n, int64_t s_band, int64_t s_row, int64_t s_col, int64_t r_n,
+                              int64_t r_band, int64_t r_row, int64_t r_col, int reduce, void *stream);
+int dtcwt_b200_reg_boxrescale(const double *qt, double *out, int64_t n, int64_t h, int64_t w, int64_t H, int64_t W,
+                              int accumulate, void *stream);
+int dtcwt_b200_reg_solve(const double *qt, double *avecs, int64_t count, int accumulate, void *stream);
+int dtcwt_b200_reg_coords(const double *avecs, double *xs, double *ys, int64_t n, int64_t H, int64_t W, int64_t h,
+                          int64_t w, int mode, void *stream);
+int dtcwt_b200_sample_f32(const float *im, float *out, const double *xs, const double *ys, int64_t n, int64_t h,
+                          int64_t w, int64_t C, int64_t oh, int64_t ow, int64_t i_n, int64_t i_y, int64_t i_x,
+                          int64_t i_c, int64_t o_n, int64_t o_y, int64_t o_x, int64_t o_c, int64_t coord_n,
+                          int is_complex, int method, int coords, const double *wx, const double *wy, void *stream);
+int dtcwt_b200_sample_f64(const double *im, double *out, const double *xs, const double *ys, int64_t n, int64_t h,
+                          int64_t w, int64_t C, int64_t oh, int64_t ow, int64_t i_n, int64_t i_y, int64_t i_x,
+                          int64_t i_c, int64_t o_n, int64_t o_y, int64_t o_x, int64_t o_c, int64_t coord_n,
+                          int is_complex, int method, int coords, const double *wx, const double *wy, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@
 #include "../../dtcwt_b200/csrc/fused2d.cuh"
 #include "../../dtcwt_b200/csrc/stream2d.cuh"
 #include "../../dtcwt_b200/csrc/fused3d.cuh"
+#include "../../dtcwt_b200/csrc/registration.cuh"
 #include "../../dtcwt_b200/csrc/axis_pass.cuh"
 
 namespace dtcwt {
@@ -125,6 +126,7 @@ static int launch_fwds1(typename K::Args& a, void* /*stream*/) {
 }  // namespace dtcwt
 
 #include "../../dtcwt_b200/csrc/abi_generic.inl"
+#include "../../dtcwt_b200/csrc/abi_reg.inl"
 #include "../../dtcwt_b200/csrc/abi_fused2d.inl"
 #include "../../dtcwt_b200/csrc/abi_axis.inl"
 #include "../../dtcwt_b200/csrc/abi_fused3d.inl"

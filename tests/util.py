@@ -53,3 +53,27 @@ def summarise_cube(M, apron=4):
     """summarise_mat applied to every axis-2 slice, stacked on axis 2 (tests/util.py:62-67)."""
     parts = [summarise_mat(M[:, :, i, ...], apron) for i in range(M.shape[2])]
     return np.dstack(parts)
+
+
+def reg_frames(shape=(192, 256), seed=5):
+    """A seeded synthetic frame pair for the registration tests: band-limited texture and a copy of it moved by a
+    smooth, mostly translational flow of about (2, 3) pixels (the reference's examples/register_images.py rolls a
+    frame; a smooth flow also exercises the affine terms).  float64 in [0, 1]."""
+    rs = np.random.RandomState(seed)
+    h, w = shape
+    F = np.fft.rfft2(rs.randn(h, w))
+    fy = np.fft.fftfreq(h)[:, None]
+    fx = np.fft.rfftfreq(w)[None, :]
+    F *= np.exp(-(fx ** 2 + fy ** 2) / (2 * 0.06 ** 2))
+    tex = np.fft.irfft2(F, s=(h, w))
+    tex = (tex - tex.min()) / (tex.max() - tex.min())
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    sx = xx - 3.0 - 1.5 * (yy / h - 0.5)
+    sy = yy - 2.0 + 1.0 * (xx / w - 0.5)
+    x0 = np.clip(np.floor(sx).astype(int), 0, w - 2)
+    y0 = np.clip(np.floor(sy).astype(int), 0, h - 2)
+    ax = np.clip(sx - x0, 0, 1)
+    ay = np.clip(sy - y0, 0, 1)
+    moved = ((1 - ay) * ((1 - ax) * tex[y0, x0] + ax * tex[y0, x0 + 1]) +
+             ay * ((1 - ax) * tex[y0 + 1, x0] + ax * tex[y0 + 1, x0 + 1]))
+    return tex, moved
