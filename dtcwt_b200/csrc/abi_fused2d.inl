@@ -103,6 +103,10 @@ typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps
 typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 2, 2> InvL1_nsbC;   // arithmetic only
 #endif
 typedef InvS1<19, 19, 0x7ffffu, 0x7ffffu, 24, 3> InvL1_19_19;       // any odd pair up to 19 taps (zero-padded)
+// the same with the inputs staged by bulk copies (ring, stages, prefetch depth); the default when rows are 16-byte aligned
+typedef InvS1T<19, 13, kMask19, kMask13, 24, 6, 4, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1> > InvT1_nsb;
+typedef InvS1T<19, 19, 0x7ffffu, 0x7ffffu, 24, 6, 4> InvT1_19_19;
+typedef InvS1T<7, 5, 0x7fu, 0x1fu, 8, 4, 3> InvT1_7_5;
 typedef InvS1<7, 5, 0x7fu, 0x1fu, 8, 2> InvL1_7_5;                  // near_sym_a (+ legall 3/5)
 // levels >= 2: q-shift pairs; every shipped family has a positive lowpass and a negative highpass tap correlation
 template <int M> struct FwdLq { typedef Fwd2d<SpecDec<M, true>, SpecDec<M, false>, 32, 16, 4> type; };
@@ -323,6 +327,25 @@ int dtcwt_b200_inv2d_level1_f32(const float* z, const float* yh, float* out, int
     const uint32_t nz1 = taps_col_s(a.g1, g1o, m1, K1, 1.0);
     pair_tab(a.p0, a.g0, K0);
     pair_tab(a.p1, a.g1, K1);
+    // inputs staged by asynchronous bulk copies when every row segment is 16-byte aligned (DTCWT_B200_INV_STAGED=0: per-thread loads)
+    const bool staged = env_int("DTCWT_B200_INV_STAGED", 1) != 0 && (cols % 4) == 0 && (zs_row % 2) == 0 && (zs_band % 2) == 0 &&
+                        (zs_n % 2) == 0 && aligned_to(z, 16) && aligned_to(yh, 16);
+    if (staged && small) {
+        a.periods = choose_periods(a.rows, InvT1_7_5::RING, (int64_t)InvT1_7_5::tiles_c(a) * a.n);
+        return launch_invs1t<InvT1_7_5>(a, stream);
+    }
+    if (staged && K1 == 13 && BakedTaps<NearSymB_g0>::same(a.g0) && BakedTaps<NearSymB_g1>::same(a.g1)) {
+        a.periods = choose_periods(a.rows, InvT1_nsb::RING, (int64_t)InvT1_nsb::tiles_c(a) * a.n);
+        return launch_invs1t<InvT1_nsb>(a, stream);
+    }
+    if (staged) {
+        if (K1 == 13) {                  // the general instance takes two 19-slot filters
+            taps_col_s(a.g1, g1o, m1, 19, 1.0);
+            pair_tab(a.p1, a.g1, 19);
+        }
+        a.periods = choose_periods(a.rows, InvT1_19_19::RING, (int64_t)InvT1_19_19::tiles_c(a) * a.n);
+        return launch_invs1t<InvT1_19_19>(a, stream);
+    }
     if (small) {
         a.periods = choose_periods(a.rows, InvL1_7_5::RING, (int64_t)InvL1_7_5::tiles_c(a) * a.n);
         return launch_invs1<InvL1_7_5>(a, stream);

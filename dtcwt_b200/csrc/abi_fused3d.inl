@@ -23,8 +23,8 @@ typedef Fwd2d<SpecCol<19, kMask19>, SpecCol<19>, 64, 64, 8, RtPhase, RtPhase, Rt
 typedef Fwd2d<SpecCol<7>, SpecCol<7>, 64, 64, 8, RtPhase, RtPhase, RtPhase, kFwdLow> FwdLow7;
 typedef Fwd2d<SpecCol<19>, SpecCol<19>, 64, 64, 8, RtPhase, RtPhase, RtPhase, kFwdLow> FwdLow19;
 // depth kernels
-template <int M> struct Z3FwdQ { typedef Z3Fwd<SpecDec<M, true>, SpecDec<M, false>, 4> type; };
-template <int M> struct Z3InvQ { typedef Z3Inv<SpecInt<M, true>, SpecInt<M, false>, 4> type; };
+template <int M> struct Z3FwdQ { typedef Z3Fwd<SpecDec<M, true>, SpecDec<M, false>, 2> type; };      // NG = 2: 72 registers, 3 CTAs per SM (measured 17 % faster than NG = 4)
+template <int M> struct Z3InvQ { typedef Z3Inv<SpecInt<M, true>, SpecInt<M, false>, 2> type; };
 typedef Z3Fwd<SpecCol<19>, SpecCol<19>, 8> Z3Fwd1;
 typedef Z3Inv<SpecCol<19>, SpecCol<19>, 8> Z3Inv1;
 
@@ -200,7 +200,7 @@ int dtcwt_b200_fwd3d_levelq_f32(const float* x, float* lll, float* yh, float* sc
     taps_dec(z.lo, lo_a, lo_b, m, true, 0.5);
     taps_dec(z.hi, hi_a, hi_b, m, false, 0.5);
     if (m == 10) return launch_z3<Z3FwdQ<10>::type>(z, stream);
-    if (m == 14 && env_int("DTCWT_B200_Z3_NG", 4) == 2) return launch_z3<Z3Fwd<SpecDec<14, true>, SpecDec<14, false>, 2> >(z, stream);
+    if (m == 14 && env_int("DTCWT_B200_Z3_NG", 2) == 4) return launch_z3<Z3Fwd<SpecDec<14, true>, SpecDec<14, false>, 4> >(z, stream);
     if (m == 14) return launch_z3<Z3FwdQ<14>::type>(z, stream);
     return launch_z3<Z3FwdQ<18>::type>(z, stream);
 }
@@ -232,7 +232,7 @@ int dtcwt_b200_inv3d_levelq_f32(const float* yl, const float* yh, float* out, fl
     taps_int(z.lo, lo_a, lo_b, m, true, 0.5);
     taps_int(z.hi, hi_a, hi_b, m, false, 0.5);
     if (m == 10) rc = launch_z3<Z3InvQ<10>::type>(z, stream);
-    else if (m == 14 && env_int("DTCWT_B200_Z3_NG", 4) == 2) rc = launch_z3<Z3Inv<SpecInt<14, true>, SpecInt<14, false>, 2> >(z, stream);
+    else if (m == 14 && env_int("DTCWT_B200_Z3_NG", 2) == 4) rc = launch_z3<Z3Inv<SpecInt<14, true>, SpecInt<14, false>, 4> >(z, stream);
     else if (m == 14) rc = launch_z3<Z3InvQ<14>::type>(z, stream);
     else rc = launch_z3<Z3InvQ<18>::type>(z, stream);
     if (rc) return rc;

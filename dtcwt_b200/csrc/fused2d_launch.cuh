@@ -4,50 +4,19 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include "async_copy.cuh"
 #include "fused2d.cuh"
 #include "stream2d.cuh"
 
 namespace dtcwt {
 
-// ------------------------------------------------------------------ TMA / mbarrier (PTX)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
+// ------------------------------------------------------------------ TMA (PTX); mbarrier primitives: async_copy.cuh
 // box [1][rows][cols] of a [n][rows][cols] tensor -> dense smem tile; out-of-range elements arrive as zeros
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
         : "memory");
-}
-
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();      // a lost transaction must not hang the GPU
-    }
 }
 
 template <class K, int PH, bool DONE = (PH >= K::kPhases)>
@@ -129,6 +98,36 @@ __global__ void __launch_bounds__(kStreamThreads, K::kMinBlocks) invs1_kernel(co
     const int np = K::run_periods(a, by);
     for (int p = 0; p < np; ++p) {
         K::cols(a, th, fused_smem, bx, by, bz, tid, p);
+        if (p > 0) {
+            __syncthreads();
+            K::rows(a, fused_smem, bx, by, bz, tid, p);
+            __syncthreads();
+        }
+    }
+}
+
+// streaming level-1 inverse with bulk-copy staged inputs (stream2d.cuh: InvS1T)
+template <class K>
+__global__ void __launch_bounds__(kStreamThreads, K::kMinBlocks) invs1t_kernel(const __grid_constant__ typename K::Args a) {
+    __shared__ __align__(8) Mbar full[K::NSTAGE], empty[K::NSTAGE];
+    const int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z, tid = threadIdx.x;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < K::NSTAGE; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kStreamThreads);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    typename K::Pipe pipe;
+    pipe.full = full;
+    pipe.empty = empty;
+    typename K::Thread th;
+    K::init(a, th, fused_smem, pipe, bx, by, bz, tid);
+    const int np = K::run_periods(a, by);
+    for (int p = 0; p < np; ++p) {
+        K::cols(a, th, fused_smem, pipe, bx, by, bz, tid, p);
         if (p > 0) {
             __syncthreads();
             K::rows(a, fused_smem, bx, by, bz, tid, p);
@@ -223,8 +222,11 @@ static int launch_fwd2d(typename K::Args& a, void* stream) {
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
     a.use_tma = 0;
-    // TMA needs a 16-byte aligned base and row pitch; other shapes take the plain-load staging phase
-    if (!tma_disabled_by_env() && (a.cols % 4) == 0 && ((uintptr_t)a.x % 16) == 0 && tensor_map_encoder()) {
+    // TMA needs a 16-byte aligned base and row pitch, and every box must START on a 16-byte boundary of its row: the
+    // first column of a tile is a multiple of 4 minus pc_lo, so two replicated columns (ext_mode 8 of the 3-D transform)
+    // rule it out -- an unaligned start never completes its transaction (measured: the mbarrier wait times out).
+    // Other shapes take the plain-load staging phase.
+    if (!tma_disabled_by_env() && (a.cols % 4) == 0 && (a.pc_lo % 4) == 0 && ((uintptr_t)a.x % 16) == 0 && tensor_map_encoder()) {
         const cuuint64_t dims[3] = {(cuuint64_t)a.cols, (cuuint64_t)a.rows, (cuuint64_t)(a.n > 0 ? a.n : 1)};
         const cuuint64_t strides[2] = {(cuuint64_t)a.cols * 4, (cuuint64_t)a.cols * a.rows * 4};
         const cuuint32_t box[3] = {(cuuint32_t)K::CX, (cuuint32_t)K::RX, 1};
@@ -283,6 +285,18 @@ static int launch_fwds1(typename K::Args& a, void* stream) {
     if (K::tiles_r(a) > 65535 || a.n > 65535) return DTCWT_B200_EUNSUPPORTED;      // grid.y / grid.z limits
     const dim3 grid((unsigned)K::tiles_c(a), (unsigned)K::tiles_r(a), (unsigned)a.n);
     fwds1_kernel<K><<<grid, K::kThreads, smem, (cudaStream_t)stream>>>(a, box);
+    return (int)cudaGetLastError();
+}
+
+template <class K>
+static int launch_invs1t(typename K::Args& a, void* stream) {
+    const size_t smem = (size_t)K::kSmemFloats * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(invs1t_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    if (a.n == 0) return DTCWT_B200_OK;
+    if (K::tiles_r(a) > 65535 || a.n > 65535) return DTCWT_B200_EUNSUPPORTED;      // grid.y / grid.z limits
+    const dim3 grid((unsigned)K::tiles_c(a), (unsigned)K::tiles_r(a), (unsigned)a.n);
+    invs1t_kernel<K><<<grid, kStreamThreads, smem, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
 

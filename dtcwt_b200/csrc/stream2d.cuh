@@ -29,6 +29,7 @@
 #pragma once
 #include <type_traits>
 
+#include "async_copy.cuh"
 #include "fused2d.cuh"
 
 namespace dtcwt {
@@ -285,6 +286,236 @@ struct InvS1 {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if (c0 + 2 * i < a.cols) *reinterpret_cast<F2*>(d + 2 * i) = acc[i];      // cols is even
+            }
+        }
+    }
+};
+
+// =============================================================================== inverse level 1, staged inputs
+// InvS1 with its eight input streams (two lowpass rows, six sub-band rows per quad row) staged in shared memory by
+// asynchronous bulk copies (cp.async.bulk, the TMA unit) instead of per-thread global loads: one elected thread per
+// step issues the eight 1 KB row segments of the quad row DEPTH steps ahead into a ring of NSTAGE stages; a `full`
+// mbarrier per stage counts the bytes as they land, an `empty` one the consumers that have taken their four values.
+// The column-pass warps never wait on a global load, DEPTH x 8 KB per CTA are in flight whatever the register
+// budget, and the prefetch registers of InvS1 are gone.  Segments are 16-byte aligned because CQ is a multiple of 4
+// (the strip's first quad column is even); on the left / right image border only the part of the segment that lies
+// inside the image is copied and the threads read their mirrored quad column (index th.idx) with the two columns
+// exchanged, exactly as InvS1 does.  The host falls back to InvS1 when rows are not 16-byte aligned.
+template <int K0, int K1, uint32_t M0, uint32_t M1, int RING_, int NSTAGE_, int DEPTH_, class T0 = ArgTaps, class T1 = ArgTaps>
+struct InvS1T {
+    typedef InvS1Args Args;
+    static constexpr int RING = RING_, PER = RING_ / 2, NSTAGE = NSTAGE_, DEPTH = DEPTH_;
+    static constexpr int C0 = (K0 - 1) / 2, C1 = (K1 - 1) / 2, CQ = round_up(C0, 4);
+    static constexpr int kThreads = kStreamThreads;
+    static constexpr int QC = kThreads / 2;
+    static constexpr int CY = 2 * QC;
+    static constexpr int CYP = CY + 4;
+    static constexpr int TWI = (CY - 2 * CQ) / 8 * 8;
+    static constexpr int NSEG = TWI / 8;
+    static constexpr int WS0 = (CQ - C0) / 4 * 4, WE0 = round_up(CQ + 8 + C0, 4);
+    static constexpr int WS1 = (CQ - C1) / 4 * 4, WE1 = round_up(CQ + 8 + C1, 4);
+    static constexpr int kYFloats = 2 * RING * CYP;
+    static constexpr int kStreamFloats = 2 * QC;                // one staged row segment: QC complex values / 2 QC reals
+    static constexpr int kStageFloats = 8 * kStreamFloats;
+    static constexpr int kSmemFloats = kYFloats + NSTAGE * kStageFloats;
+    static constexpr int kMinBlocks = 2;
+    static_assert(K0 >= K1 && (K0 & 1) && (K1 & 1) && K0 <= kStreamMaxTaps && (M0 & 1u), "filter pair");
+    static_assert(RING >= CQ + C0 + 1 && (RING % 2) == 0 && (PER % NSTAGE) == 0 && DEPTH >= 1 && DEPTH < NSTAGE, "ring / pipeline");
+    static_assert(8 * (NSEG - 1) + WE0 <= CY && 8 * (NSEG - 1) + WE1 <= CY, "row-pass window inside the smem row");
+    static_assert((kYFloats % 4) == 0 && (TWI % 4) == 0 && (CQ % 4) == 0, "16-byte aligned stages and segments");
+
+    struct Raw { F2 v[4]; };       // role 0: Z top row, Z bottom row, band 0, band 5;  role 1: bands 2, 3, 1, 4
+    struct Thread {
+        F2 acc[RING];
+        int idx;                   // this thread's (mirrored) quad column inside a staged segment
+        int fc;
+    };
+    struct Pipe { Mbar* full; Mbar* empty; };
+
+    static DTCWT_HD int run_rows(const Args& a) { return RING * a.periods; }
+    static DTCWT_HD int tiles_c(const Args& a) { return (a.cols + TWI - 1) / TWI; }
+    static DTCWT_HD int tiles_r(const Args& a) { return (a.rows + run_rows(a) - 1) / run_rows(a); }
+    static DTCWT_HD int run_periods(const Args& a, int by) {
+        const int left = a.rows - run_rows(a) * by;
+        const int e = (left + RING - 1) / RING;
+        return 1 + (e < a.periods ? e : a.periods);
+    }
+    static DTCWT_HD int quad_base(const Args& a, int by, int p) { return (run_rows(a) * by - RING + CQ) / 2 + PER * p; }
+    static DTCWT_HD bool edge_period(const Args& a, int by, int p) {
+        const int qb = quad_base(a, by, p);
+        return qb < 0 || (qb + PER > a.rows / 2);
+    }
+    static DTCWT_HD bool col_edge(const Args& a, int bx) { return (TWI * bx - CQ < 0) || (TWI * bx - CQ + CY > a.cols); }
+    static DTCWT_HD int first_quad(int bx) { return (TWI * bx - CQ) / 2; }        // exact: both even; may be negative
+
+    // ONE thread: issue the eight row segments of step g (quad row quad_base(by, 0) + g, folded into the image)
+#ifdef DTCWT_EMU
+    static void produce(const Args& a, float* sm, const Pipe& pipe, int bx, int by, int bz, int g) {
+#else
+    static __device__ __noinline__ void produce(const Args& a, float* sm, const Pipe& pipe, int bx, int by, int bz, int g) {
+#endif
+        const int stage = g % NSTAGE;
+        bool f;
+        const int q = fold_quad(quad_base(a, by, 0) + g, a.rows / 2, f);
+        const int g0 = first_quad(bx), nq = a.cols / 2;
+        const int s0 = g0 < 0 ? 0 : g0;
+        const int s1 = (g0 + QC < nq) ? g0 + QC : nq;
+        const uint32_t bytes = (uint32_t)(s1 - s0) * 8u;
+        if (g >= NSTAGE) mbar_wait(&pipe.empty[stage], (uint32_t)((g / NSTAGE) - 1) & 1u);     // every consumer has taken the stage's previous content
+        mbar_expect_tx(&pipe.full[stage], 8u * bytes);
+        float* st = sm + kYFloats + stage * kStageFloats + 2 * (s0 - g0);
+        const float* zrow = a.z + ((int64_t)bz * a.rows + 2 * q) * a.cols + 2 * s0;
+        bulk_copy(st, zrow, bytes, &pipe.full[stage]);
+        bulk_copy(st + kStreamFloats, zrow + a.cols, bytes, &pipe.full[stage]);
+        const float* yb = a.yh + 2 * ((int64_t)bz * a.zs_n + (int64_t)q * a.zs_row + s0);
+        bulk_copy(st + 2 * kStreamFloats, yb, bytes, &pipe.full[stage]);
+        bulk_copy(st + 3 * kStreamFloats, yb + 2 * 5 * a.zs_band, bytes, &pipe.full[stage]);
+        bulk_copy(st + 4 * kStreamFloats, yb + 2 * 2 * a.zs_band, bytes, &pipe.full[stage]);
+        bulk_copy(st + 5 * kStreamFloats, yb + 2 * 3 * a.zs_band, bytes, &pipe.full[stage]);
+        bulk_copy(st + 6 * kStreamFloats, yb + 2 * 1 * a.zs_band, bytes, &pipe.full[stage]);
+        bulk_copy(st + 7 * kStreamFloats, yb + 2 * 4 * a.zs_band, bytes, &pipe.full[stage]);
+    }
+
+    static DTCWT_D void init(const Args& a, Thread& th, float* sm, const Pipe& pipe, int bx, int by, int bz, int tid) {
+        const int qc = tid % QC;
+        bool fc;
+        int gj = fold_quad(first_quad(bx) + qc, a.cols / 2, fc);
+        th.fc = fc ? 1 : 0;
+        // quad columns far outside the image only feed outputs that are never stored: keep them inside the copied part
+        const int g0 = first_quad(bx), nq = a.cols / 2;
+        const int s0 = g0 < 0 ? 0 : g0, s1 = (g0 + QC < nq) ? g0 + QC : nq;
+        gj = gj < s0 ? s0 : (gj >= s1 ? s1 - 1 : gj);
+        th.idx = gj - g0;
+#pragma unroll
+        for (int i = 0; i < RING; ++i) th.acc[i] = zero2();
+        if (tid == 0) {
+            const int total = run_periods(a, by) * PER;
+            for (int g = 0; g < DEPTH && g < total; ++g) produce(a, sm, pipe, bx, by, bz, g);
+        }
+    }
+
+    static DTCWT_D void c2q_rows(const F2 w0, const F2 w1, float g0, float g1, F2& top, F2& bot) {
+        const float r0 = w0.x * g0, i0 = w0.y * g0;
+        top.x = fmaf(w1.x, g1, r0); top.y = fmaf(w1.y, g1, i0);
+        bot.x = fmaf(-w1.y, g1, i0); bot.y = fmaf(w1.x, g1, -r0);
+    }
+    static DTCWT_D void flip_quad(bool fr, bool fc, F2& top, F2& bot) {
+        if (fc) { float t; t = top.x; top.x = top.y; top.y = t; t = bot.x; bot.x = bot.y; bot.y = t; }
+        if (fr) { const F2 t = top; top = bot; bot = t; }
+    }
+
+    // step u of period p for one thread: take the staged quad row, c2q, scatter into the ring, emit two finished rows
+    template <int ROLE, bool EDGE>
+    static DTCWT_D void step_role(const Args& a, Thread& th, float* sm, const Pipe& pipe, int bx, int by, int bz, int tid, int p,
+                                  const int u, bool cedge) {
+        const int g = p * PER + u;
+        const int stage = u % NSTAGE;                              // PER is a multiple of NSTAGE
+        const int total = run_periods(a, by) * PER;
+        if (tid == 32 * (u % (kThreads / 32)) && g + DEPTH < total) produce(a, sm, pipe, bx, by, bz, g + DEPTH);
+        mbar_wait(&pipe.full[stage], (uint32_t)(g / NSTAGE) & 1u);
+        const float* st = sm + kYFloats + stage * kStageFloats + (4 * ROLE) * kStreamFloats + 2 * th.idx;
+        Raw cur;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur.v[i] = *reinterpret_cast<const F2*>(st + i * kStreamFloats);
+        mbar_arrive(&pipe.empty[stage]);
+        const int qb = quad_base(a, by, p);
+        const bool emit = p > 0;
+        const float ga0 = a.gain[ROLE == 0 ? 0 : 2], ga1 = a.gain[ROLE == 0 ? 5 : 3];
+        const float gb0 = a.gain[1], gb1 = a.gain[4];
+        float* y = sm + ROLE * (RING * CYP) + 2 * (tid % QC);
+        F2 at, ab, bt, bb;
+        if (ROLE == 0) {
+            at = cur.v[0]; ab = cur.v[1];
+            c2q_rows(cur.v[2], cur.v[3], ga0, ga1, bt, bb);
+        } else {
+            c2q_rows(cur.v[0], cur.v[1], ga0, ga1, at, ab);
+            c2q_rows(cur.v[2], cur.v[3], gb0, gb1, bt, bb);
+        }
+        if (EDGE) {
+            bool fr;
+            fold_quad(qb + u, a.rows / 2, fr);
+            flip_quad(fr, false, at, ab);
+            flip_quad(fr, false, bt, bb);
+        }
+        if (cedge) {
+            flip_quad(false, th.fc != 0, at, ab);
+            flip_quad(false, th.fc != 0, bt, bb);
+        }
+        ring_scatter<T0, K0, M0, C0, true, RING>(2 * u, at, a.g0, th.acc);
+        ring_scatter<T1, K1, M1, C1, false, RING>(2 * u, bt, a.g1, th.acc);
+        if (emit) {
+            *reinterpret_cast<F2*>(y + (2 * u) * CYP) = th.acc[pmod(2 * u - CQ, RING)];
+            *reinterpret_cast<F2*>(y + (2 * u + 1) * CYP) = th.acc[pmod(2 * u + 1 - CQ, RING)];
+        }
+        ring_scatter<T0, K0, M0, C0, true, RING>(2 * u + 1, ab, a.g0, th.acc);
+        ring_scatter<T1, K1, M1, C1, false, RING>(2 * u + 1, bb, a.g1, th.acc);
+    }
+
+    static DTCWT_D void step(const Args& a, Thread& th, float* sm, const Pipe& pipe, int bx, int by, int bz, int tid, int p, const int u) {
+        const int role = tid / QC;                                 // uniform within a warp
+        const bool edge = edge_period(a, by, p), cedge = col_edge(a, bx);
+        if (role == 0) {
+            if (edge) step_role<0, true>(a, th, sm, pipe, bx, by, bz, tid, p, u, cedge);
+            else step_role<0, false>(a, th, sm, pipe, bx, by, bz, tid, p, u, cedge);
+        } else {
+            if (edge) step_role<1, true>(a, th, sm, pipe, bx, by, bz, tid, p, u, cedge);
+            else step_role<1, false>(a, th, sm, pipe, bx, by, bz, tid, p, u, cedge);
+        }
+    }
+
+    template <int ROLE, bool EDGE>
+    static DTCWT_D void cols_role(const Args& a, Thread& th, float* sm, const Pipe& pipe, int bx, int by, int bz, int tid, int p, bool cedge) {
+#pragma unroll
+        for (int u = 0; u < PER; ++u) step_role<ROLE, EDGE>(a, th, sm, pipe, bx, by, bz, tid, p, u, cedge);
+    }
+    // column pass of period p (device: the PER steps unrolled, ring indices static)
+    static DTCWT_D void cols(const Args& a, Thread& th, float* sm, const Pipe& pipe, int bx, int by, int bz, int tid, int p) {
+        const int role = tid / QC;
+        const bool edge = edge_period(a, by, p), cedge = col_edge(a, bx);
+        if (role == 0) {
+            if (edge) cols_role<0, true>(a, th, sm, pipe, bx, by, bz, tid, p, cedge);
+            else cols_role<0, false>(a, th, sm, pipe, bx, by, bz, tid, p, cedge);
+        } else {
+            if (edge) cols_role<1, true>(a, th, sm, pipe, bx, by, bz, tid, p, cedge);
+            else cols_role<1, false>(a, th, sm, pipe, bx, by, bz, tid, p, cedge);
+        }
+    }
+
+    // row pass of period p (p > 0): out = H:g0(y1) + H:g1(y2) on the RING rows the column pass just finished
+    static DTCWT_D void rows(const Args& a, float* sm, int bx, int by, int bz, int tid, int p) {
+        const float* y1 = sm;
+        const float* y2 = sm + RING * CYP;
+        float* img = a.out + (int64_t)bz * a.rows * a.cols;
+        const int r0 = run_rows(a) * by + RING * (p - 1);
+        int rp = (tid >> 1) / NSEG, seg = (tid >> 1) % NSEG;
+#pragma unroll 1
+        for (int task = tid; task < RING * NSEG; task += kThreads, rp += (kThreads / 2) / NSEG, seg += (kThreads / 2) % NSEG) {
+            if (seg >= NSEG) { seg -= NSEG; ++rp; }
+            const int yr = 2 * rp + (tid & 1);
+            const int r = r0 + yr, c0 = TWI * bx + 8 * seg;
+            if (r >= a.rows || c0 >= a.cols) continue;
+            F2 acc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = zero2();
+            const F4* s1 = reinterpret_cast<const F4*>(y1 + yr * CYP + 8 * seg + WS0);
+            const F4* s2 = reinterpret_cast<const F4*>(y2 + yr * CYP + 8 * seg + WS1);
+#pragma unroll
+            for (int c = 0; c < (WE0 - WS0) / 4; ++c)
+                pair_gather4<K0, M0, C0, WS0 - CQ, 8, WE0 - WS0>(4 * c, s1[c], a.p0, acc);
+#pragma unroll
+            for (int c = 0; c < (WE1 - WS1) / 4; ++c)
+                pair_gather4<K1, M1, C1, WS1 - CQ, 8, WE1 - WS1>(4 * c, s2[c], a.p1, acc);
+            float* d = img + (int64_t)r * a.cols + c0;
+            if (a.out_vec4 && c0 + 8 <= a.cols) {
+                F4 v;
+                v.x = acc[0].x; v.y = acc[0].y; v.z = acc[1].x; v.w = acc[1].y;
+                reinterpret_cast<F4*>(d)[0] = v;
+                v.x = acc[2].x; v.y = acc[2].y; v.z = acc[3].x; v.w = acc[3].y;
+                reinterpret_cast<F4*>(d)[1] = v;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (c0 + 2 * i < a.cols) *reinterpret_cast<F2*>(d + 2 * i) = acc[i];
             }
         }
     }

@@ -103,6 +103,32 @@ static int launch_invs1(typename K::Args& a, void* /*stream*/) {
     return DTCWT_B200_OK;
 }
 
+// Staged streaming kernel: the device issues the bulk copies of step g + DEPTH from inside step g; here every step of a
+// period is run for all threads in turn, so a stage is always filled (by that step's issuer thread) DEPTH steps before
+// it is read and never while another thread of the same step reads it (DEPTH < NSTAGE).
+template <class K>
+static int launch_invs1t(typename K::Args& a, void* /*stream*/) {
+    std::vector<float> sm(K::kSmemFloats);
+    std::vector<typename K::Thread> th(K::kThreads);
+    typename K::Pipe pipe;
+    pipe.full = nullptr;
+    pipe.empty = nullptr;
+    for (int bz = 0; bz < a.n; ++bz)
+        for (int by = 0; by < K::tiles_r(a); ++by)
+            for (int bx = 0; bx < K::tiles_c(a); ++bx) {
+                for (size_t i = 0; i < sm.size(); ++i) sm[i] = NAN;
+                for (int tid = 0; tid < K::kThreads; ++tid) K::init(a, th[tid], sm.data(), pipe, bx, by, bz, tid);
+                const int np = K::run_periods(a, by);
+                for (int p = 0; p < np; ++p) {
+                    for (int u = 0; u < K::PER; ++u)
+                        for (int tid = 0; tid < K::kThreads; ++tid) K::step(a, th[tid], sm.data(), pipe, bx, by, bz, tid, p, u);
+                    if (p > 0)
+                        for (int tid = 0; tid < K::kThreads; ++tid) K::rows(a, sm.data(), bx, by, bz, tid, p);
+                }
+            }
+    return DTCWT_B200_OK;
+}
+
 template <class K>
 static int launch_fwds1(typename K::Args& a, void* /*stream*/) {
     std::vector<float> sm(K::kSmemFloats);
