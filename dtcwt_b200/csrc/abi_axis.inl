@@ -43,7 +43,7 @@ static int axis_dec_m(AxisArgs& a, bool pos, void* stream) {
 
 static int axis_coldfilt(const float* x, float* y, int64_t outer, int64_t len, int64_t inner, int pad_lo, int pad_hi,
                          const double* ha, const double* hb, int m, int accumulate, void* stream) {
-    if ((m != 10 && m != 14 && m != 18) || env_int("DTCWT_B200_NO_AXIS", 0)) return DTCWT_B200_EUNSUPPORTED;
+    if ((m != 10 && m != 14 && m != 16 && m != 18) || env_int("DTCWT_B200_NO_AXIS", 0)) return DTCWT_B200_EUNSUPPORTED;
     AxisArgs a;
     if (!axis_common(a, x, y, outer, len, inner)) return DTCWT_B200_EUNSUPPORTED;
     a.pad_lo = pad_lo; a.L = (int)len + pad_lo + pad_hi; a.Lout = a.L / 2; a.crop = 0; a.accumulate = accumulate;
@@ -52,6 +52,7 @@ static int axis_coldfilt(const float* x, float* y, int64_t outer, int64_t len, i
     taps_dec(a.t, ha, hb, m, pos, 1.0);
     if (m == 10) return axis_dec_m<10>(a, pos, stream);
     if (m == 14) return axis_dec_m<14>(a, pos, stream);
+    if (m == 16) return axis_dec_m<16>(a, pos, stream);
     return axis_dec_m<18>(a, pos, stream);
 }
 
@@ -63,7 +64,7 @@ static int axis_int_m(AxisArgs& a, bool pos, void* stream) {
 
 static int axis_colifilt(const float* x, float* y, int64_t outer, int64_t len, int64_t inner, int crop,
                          const double* ha, const double* hb, int m, int accumulate, void* stream) {
-    if ((m != 10 && m != 14 && m != 18) || env_int("DTCWT_B200_NO_AXIS", 0)) return DTCWT_B200_EUNSUPPORTED;
+    if ((m != 10 && m != 14 && m != 16 && m != 18) || env_int("DTCWT_B200_NO_AXIS", 0)) return DTCWT_B200_EUNSUPPORTED;
     AxisArgs a;
     if (!axis_common(a, x, y, outer, len, inner)) return DTCWT_B200_EUNSUPPORTED;
     a.pad_lo = 0; a.L = (int)len; a.Lout = 2 * (int)len - 2 * crop; a.crop = crop; a.accumulate = accumulate;
@@ -71,6 +72,7 @@ static int axis_colifilt(const float* x, float* y, int64_t outer, int64_t len, i
     taps_int(a.t, ha, hb, m, pos);
     if (m == 10) return axis_int_m<10>(a, pos, stream);
     if (m == 14) return axis_int_m<14>(a, pos, stream);
+    if (m == 16) return axis_int_m<16>(a, pos, stream);
     return axis_int_m<18>(a, pos, stream);
 }
 

@@ -105,6 +105,7 @@ typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps
 typedef InvS1<19, 19, 0x7ffffu, 0x7ffffu, 24, 3> InvL1_19_19;       // any odd pair up to 19 taps (zero-padded)
 // the same with the inputs staged by bulk copies (ring, stages, prefetch depth); the default when rows are 16-byte aligned
 typedef InvS1T<19, 13, kMask19, kMask13, 24, 6, 4, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1> > InvT1_nsb;
+typedef InvS1T<19, 13, kMask19, kMask13, 24, 6, 5, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1> > InvT1_nsb5;   // experiment: DTCWT_B200_INV_DEPTH=5
 typedef InvS1T<19, 19, 0x7ffffu, 0x7ffffu, 24, 6, 4> InvT1_19_19;
 typedef InvS1T<7, 5, 0x7fu, 0x1fu, 8, 4, 3> InvT1_7_5;
 typedef InvS1<7, 5, 0x7fu, 0x1fu, 8, 2> InvL1_7_5;                  // near_sym_a (+ legall 3/5)
@@ -230,7 +231,7 @@ int dtcwt_b200_fwd2d_levelq_f32(const float* x, float* lolo, float* yh, int64_t 
                                 void* stream) {
     if (!lo_a || !lo_b || !hi_a || !hi_b || m < 2 || (m & 1) || pad_r < 0 || pad_r > 1 || pad_c < 0 || pad_c > 1)
         return DTCWT_B200_EINVAL;
-    if (m != 10 && m != 14 && m != 18) return DTCWT_B200_EUNSUPPORTED;
+    if (m != 10 && m != 14 && m != 16 && m != 18) return DTCWT_B200_EUNSUPPORTED;
     if (!(tap_dot(lo_a, lo_b, m) > 0) || (tap_dot(hi_a, hi_b, m) > 0)) return DTCWT_B200_EUNSUPPORTED;
     Fwd2dArgs a;
     const int rc = fwd_common(a, x, lolo, yh, n, rows, cols, pad_r, pad_r, pad_c, pad_c, 2, 4, zs_n, zs_band, zs_row);
@@ -248,6 +249,7 @@ int dtcwt_b200_fwd2d_levelq_f32(const float* x, float* lolo, float* yh, int64_t 
     }
     if (m == 10) return launch_fwd2d<FwdLq<10>::type>(a, stream);
     if (m == 14) return launch_fwd2d<FwdLq<14>::type>(a, stream);
+    if (m == 16) return launch_fwd2d<FwdLq<16>::type>(a, stream);
     return launch_fwd2d<FwdLq<18>::type>(a, stream);
 }
 #endif  // DTCWT_EMIT_FWD2D
@@ -260,7 +262,7 @@ int dtcwt_b200_inv2d_levelq_f32(const float* z, const float* yh, float* out, int
                                 const double* hi_b, int m, const double* gain, int64_t zs_n, int64_t zs_band,
                                 int64_t zs_row, void* stream) {
     if (!lo_a || !lo_b || !hi_a || !hi_b || m < 2 || (m & 1)) return DTCWT_B200_EINVAL;
-    if (m != 10 && m != 14 && m != 18) return DTCWT_B200_EUNSUPPORTED;
+    if (m != 10 && m != 14 && m != 16 && m != 18) return DTCWT_B200_EUNSUPPORTED;
     if (!(tap_dot(lo_a, lo_b, m) > 0) || (tap_dot(hi_a, hi_b, m) > 0)) return DTCWT_B200_EUNSUPPORTED;
     Inv2dArgs a;
     const int rc = inv_common(a, z, yh, out, n, rows, cols, crop_r, crop_c, 4, 2, gain, zs_n, zs_band, zs_row);
@@ -299,6 +301,7 @@ int dtcwt_b200_inv2d_levelq_f32(const float* z, const float* yh, float* out, int
     }
     if (m == 10) return launch_inv2d<InvLq<10>::type>(a, stream);
     if (m == 14) return launch_inv2d<InvLq<14>::type>(a, stream);
+    if (m == 16) return launch_inv2d<InvLq<16>::type>(a, stream);
     return launch_inv2d<InvLq<18>::type>(a, stream);
 }
 #endif  // DTCWT_EMIT_INV2D_Q
@@ -336,6 +339,7 @@ int dtcwt_b200_inv2d_level1_f32(const float* z, const float* yh, float* out, int
     }
     if (staged && K1 == 13 && BakedTaps<NearSymB_g0>::same(a.g0) && BakedTaps<NearSymB_g1>::same(a.g1)) {
         a.periods = choose_periods(a.rows, InvT1_nsb::RING, (int64_t)InvT1_nsb::tiles_c(a) * a.n);
+        if (env_int("DTCWT_B200_INV_DEPTH", 4) == 5) return launch_invs1t<InvT1_nsb5>(a, stream);
         return launch_invs1t<InvT1_nsb>(a, stream);
     }
     if (staged) {

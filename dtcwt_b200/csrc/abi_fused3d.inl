@@ -168,7 +168,7 @@ int dtcwt_b200_fwd3d_levelq_f32(const float* x, float* lll, float* yh, float* sc
     if (!lo_a || !lo_b || !hi_a || !hi_b || m < 2 || (m & 1) || pad0 < 0 || pad0 > 2 || pad1 < 0 || pad1 > 2 || pad2 < 0 ||
         pad2 > 2 || !chan_strides_ok(zs_n, zs_chan, zs_0, zs_1, zs_2))
         return DTCWT_B200_EINVAL;
-    if (m != 10 && m != 14 && m != 18) return DTCWT_B200_EUNSUPPORTED;
+    if (m != 10 && m != 14 && m != 16 && m != 18) return DTCWT_B200_EUNSUPPORTED;
     if (!(tap_dot(lo_a, lo_b, m) > 0) || (tap_dot(hi_a, hi_b, m) > 0)) return DTCWT_B200_EUNSUPPORTED;
     const int64_t L0 = d0 + 2 * pad0, L1 = d1 + 2 * pad1, L2 = d2 + 2 * pad2;
     if ((L0 % 4) || (L1 % 4) || (L2 % 4)) return DTCWT_B200_EINVAL;
@@ -190,6 +190,7 @@ int dtcwt_b200_fwd3d_levelq_f32(const float* x, float* lll, float* yh, float* sc
     }
     if (m == 10) rc = launch_fwd2d<FwdLqRaw<10>::type>(a, stream);
     else if (m == 14) rc = launch_fwd2d<FwdLqRaw<14>::type>(a, stream);
+    else if (m == 16) rc = launch_fwd2d<FwdLqRaw<16>::type>(a, stream);
     else rc = launch_fwd2d<FwdLqRaw<18>::type>(a, stream);
     if (rc) return rc;
     Z3Args z;
@@ -202,6 +203,7 @@ int dtcwt_b200_fwd3d_levelq_f32(const float* x, float* lll, float* yh, float* sc
     if (m == 10) return launch_z3<Z3FwdQ<10>::type>(z, stream);
     if (m == 14 && env_int("DTCWT_B200_Z3_NG", 2) == 4) return launch_z3<Z3Fwd<SpecDec<14, true>, SpecDec<14, false>, 4> >(z, stream);
     if (m == 14) return launch_z3<Z3FwdQ<14>::type>(z, stream);
+    if (m == 16) return launch_z3<Z3FwdQ<16>::type>(z, stream);
     return launch_z3<Z3FwdQ<18>::type>(z, stream);
 }
 
@@ -216,7 +218,7 @@ int dtcwt_b200_inv3d_levelq_f32(const float* yl, const float* yh, float* out, fl
         crop2 > 2 || !chan_strides_ok(zs_n, zs_chan, zs_0, zs_1, zs_2))
         return DTCWT_B200_EINVAL;
     if ((a0 & 1) || (a1 & 1) || (a2 & 1)) return DTCWT_B200_EINVAL;
-    if (m != 10 && m != 14 && m != 18) return DTCWT_B200_EUNSUPPORTED;
+    if (m != 10 && m != 14 && m != 16 && m != 18) return DTCWT_B200_EUNSUPPORTED;
     if (!(tap_dot(lo_a, lo_b, m) > 0) || (tap_dot(hi_a, hi_b, m) > 0)) return DTCWT_B200_EUNSUPPORTED;
     int rc = volume_check(n, a0, a1, a2, yl, yh, out, scratch, kFused3dMinSideInv);
     if (rc) return rc;
@@ -234,6 +236,7 @@ int dtcwt_b200_inv3d_levelq_f32(const float* yl, const float* yh, float* out, fl
     if (m == 10) rc = launch_z3<Z3InvQ<10>::type>(z, stream);
     else if (m == 14 && env_int("DTCWT_B200_Z3_NG", 2) == 4) rc = launch_z3<Z3Inv<SpecInt<14, true>, SpecInt<14, false>, 4> >(z, stream);
     else if (m == 14) rc = launch_z3<Z3InvQ<14>::type>(z, stream);
+    else if (m == 16) rc = launch_z3<Z3InvQ<16>::type>(z, stream);
     else rc = launch_z3<Z3InvQ<18>::type>(z, stream);
     if (rc) return rc;
     Inv2dArgs a;
@@ -248,6 +251,7 @@ int dtcwt_b200_inv3d_levelq_f32(const float* yl, const float* yh, float* out, fl
     taps_int(a.g1, hi_a, hi_b, m, false);
     if (m == 10) return launch_inv2d<InvLqRaw<10>::type>(a, stream);
     if (m == 14) return launch_inv2d<InvLqRaw<14>::type>(a, stream);
+    if (m == 16) return launch_inv2d<InvLqRaw<16>::type>(a, stream);
     return launch_inv2d<InvLqRaw<18>::type>(a, stream);
 }
 

@@ -18,6 +18,7 @@ inline void mbar_expect_tx(Mbar*, uint32_t) {}
 inline void mbar_arrive(Mbar*) {}
 inline void mbar_wait(Mbar*, uint32_t) {}
 inline void bulk_copy(void* dst, const void* src, uint32_t bytes, Mbar*) { memcpy(dst, src, bytes); }
+inline void warp_release(Mbar*, int) {}
 #else
 typedef uint64_t Mbar;
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -58,6 +59,11 @@ __device__ __forceinline__ void bulk_copy(void* dst, const void* src, uint32_t b
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// every lane of the warp has finished reading a stage (its shared-memory loads have returned): lane 0 arrives for all
+__device__ __forceinline__ void warp_release(Mbar* bar, int tid) {
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(bar);
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif

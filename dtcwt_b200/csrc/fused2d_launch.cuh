@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kStreamThreads, K::kMinBlocks) invs1t_kernel(c
 #pragma unroll
         for (int s = 0; s < K::NSTAGE; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kStreamThreads);
+            mbar_init(&empty[s], kStreamThreads / 32);      // one arrival per consumer warp
         }
         fence_mbar_init();
     }

@@ -417,7 +417,7 @@ struct InvS1T {
         Raw cur;
 #pragma unroll
         for (int i = 0; i < 4; ++i) cur.v[i] = *reinterpret_cast<const F2*>(st + i * kStreamFloats);
-        mbar_arrive(&pipe.empty[stage]);
+        warp_release(&pipe.empty[stage], tid);                  // ONE arrival per warp: 256 arrivals on one barrier word serialise
         const int qb = quad_base(a, by, p);
         const bool emit = p > 0;
         const float ga0 = a.gain[ROLE == 0 ? 0 : 2], ga1 = a.gain[ROLE == 0 ? 5 : 3];

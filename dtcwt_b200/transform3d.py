@@ -112,9 +112,15 @@ class Transform3d(object):
                 if any(int(s) % mult for s in Yl.shape[1:]):
                     raise ValueError("Input shape should be a multiple of %d in each direction when "
                                      "self.ext_mode == %d" % (mult, self.ext_mode))
-                if t["h0o"].shape[0] % 2 == 0 or t["h1o"].shape[0] % 2 == 0:
-                    raise ValueError("even-length biorthogonal filters are not supported by the 3-D transform yet")
-                if discard_level_1:
+                even = t["h0o"].shape[0] % 2 == 0
+                if even != (t["h1o"].shape[0] % 2 == 0):
+                    raise ValueError("level-1 lowpass and highpass filters must both have odd or both have even length")
+                if even and discard_level_1:
+                    raise ValueError("discard_level_1 needs odd-length level-1 filters (the reference's "
+                                     "_level1_xfm_no_highpass writes n+1 samples into n, transform3d.py:304-313)")
+                if even:
+                    Yl, Yh[0] = self._split_even(Yl, t)
+                elif discard_level_1:
                     fused = _ops.lowpass3d(Yl, t["h0o"])
                     if fused is not None:
                         Yl = fused
@@ -146,6 +152,45 @@ class Transform3d(object):
         return Pyramid(Yl, views, tuple(Ysc)) if include_scale else Pyramid(Yl, views)
 
     @staticmethod
+    def _split_even(X, t):
+        """Level 1 with even-length taps (e.g. Haar; reference transform3d.py:223-251, tests/test_xfm3.py:42-58): every
+        axis pass returns n+1 samples, LLL keeps them all and the seven highpass octants are read back at the ORIGINAL
+        size (the reference's x*a / x*b slices, :232-237, 280-288)."""
+        n, d0, d1, d2 = X.shape
+        parts = {(): X}
+        for ax in (3, 2, 1):
+            nxt = {}
+            for key, A in parts.items():
+                nxt[(0,) + key] = _ops.colfilter(A, t["h0o"], ax)
+                nxt[(1,) + key] = _ops.colfilter(A, t["h1o"], ax)
+            parts = nxt
+        lll = parts[(0, 0, 0)]
+        yh = _ops.new_highpass(n, 28, (d0 // 2, d1 // 2, d2 // 2), lll.dtype, lll.device)
+        for i, o in enumerate(_OCTANTS):
+            _ops.cube2c(parts.pop(o)[:, :d0, :d1, :d2].contiguous(), yh, 4 * i)
+        return lll, yh
+
+    @staticmethod
+    def _merge_even(Yl, yh, t):
+        """Inverse of :meth:`_split_even` (reference transform3d.py:385-440 with an even-length filter): every merge reads
+        the first n samples of its axis (:408-413) and returns n+1; the first row / column / slice is dropped (:437-438)."""
+        n, a0, a1, a2 = (int(s) for s in (yh.shape[0], 2 * yh.shape[2], 2 * yh.shape[3], 2 * yh.shape[4]))
+        if tuple(Yl.shape) != (n, a0 + 1, a1 + 1, a2 + 1):
+            raise ValueError("lowpass and highpass sizes are not valid for the inverse 3-D transform")
+        parts = {(0, 0, 0): Yl[:, :a0, :a1, :a2].contiguous()}
+        for i, o in enumerate(_OCTANTS):
+            parts[o] = _ops.c2cube(yh, 4 * i)
+        for ax in (1, 0, 2):
+            nxt = {}
+            for key in [k for k in parts if k[ax] == 0]:
+                other = tuple(1 if i == ax else key[i] for i in range(3))
+                out = _ops.colfilter(parts[key], t["g0o"], ax + 1)
+                _ops.colfilter(parts[other], t["g1o"], ax + 1, out=out, accumulate=True)
+                nxt[key] = out
+            parts = nxt
+        return parts[(0, 0, 0)][:, 1:, 1:, 1:].contiguous()
+
+    @staticmethod
     def _split(X, filt):
         """One analysis level: lo/hi along axis 2, then 1, then 0 (tensor axes 3, 2, 1) -> LLL + 28 bands."""
         parts = {(): X}
@@ -174,6 +219,8 @@ class Transform3d(object):
                     if fused is None:
                         for ax in (2, 1, 3):     # reference _level1_ifm_no_highpass :442-456, axes 1, 0, 2
                             Yl = _ops.colfilter(Yl, t["g0o"], ax)
+                elif t["g0o"].shape[0] % 2 == 0:
+                    fused = self._merge_even(Yl, Yh[0], t)
                 else:
                     self._check_sizes(Yl, Yh[0])
                     fused = _ops.inv3d_level1(Yl, Yh[0], t["g0o"], t["g1o"])

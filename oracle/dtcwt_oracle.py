@@ -484,10 +484,6 @@ class Transform3d(object):
             return _along(filt, A, ax, *lo), _along(filt, A, ax, *hi)
 
         even = level1 and (np.asarray(lo[0]).size % 2 == 0)
-        if even:
-            # even-length level-1 taps give one extra sample per axis; the reference then
-            # keeps n+1 lowpass samples but only the first n highpass ones (transform3d.py:223-251)
-            raise NotImplementedError("even-length biort in the 3-D oracle")
         parts = {(): X}
         for ax in (2, 1, 0):
             nxt = {}
@@ -498,7 +494,14 @@ class Transform3d(object):
             parts = nxt
         # keys are now (axis0, axis1, axis2) filter types
         Yl = parts[(0, 0, 0)]
-        Yh = np.concatenate([cube2c(parts[o]) for o in _OCTANTS], axis=3)
+        if even:
+            # even-length level-1 taps (e.g. Haar, tests/test_xfm3.py:42-58) give n+1 samples per axis: the reference's
+            # work cube has one extra row per octant (transform3d.py:223-224); LLL keeps all n+1, the seven highpass
+            # octants are read back through the x*a / x*b slices of the ORIGINAL size n (:232-237, :280-288)
+            n0, n1, n2 = X.shape
+            Yh = np.concatenate([cube2c(parts[o][:n0, :n1, :n2]) for o in _OCTANTS], axis=3)
+        else:
+            Yh = np.concatenate([cube2c(parts[o]) for o in _OCTANTS], axis=3)
         return Yl, Yh
 
     # ---- inverse
@@ -533,6 +536,21 @@ class Transform3d(object):
         parts = {(0, 0, 0): Yl}
         for n, o in enumerate(_OCTANTS):
             parts[o] = c2cube(Yh[..., 4 * n:4 * n + 4])
+        even = filt is colfilter and (np.asarray(lo[0]).size % 2 == 0)
+        if even:
+            # transform3d.py:385-440 with an even-length filter: every merge reads only the first n samples of an axis
+            # (the x*a / x*b slices, :408-413, 429, 431, 436), each merge returns n+1 of them, and the first row / column /
+            # slice of the result is dropped (:437-438)
+            n0, n1, n2 = parts[_OCTANTS[0]].shape
+            parts[(0, 0, 0)] = Yl[:n0, :n1, :n2]
+            for ax in (1, 0, 2):
+                nxt = {}
+                for key, A in parts.items():
+                    if key[ax] == 0:
+                        other = tuple(1 if i == ax else key[i] for i in range(3))
+                        nxt[key] = _along(filt, A, ax, *lo) + _along(filt, parts[other], ax, *hi)
+                parts = nxt
+            return parts[(0, 0, 0)][1:, 1:, 1:]
         # merge axis 1, then axis 0, then axis 2 (transform3d.py:485-495); a merged
         # axis keeps key 0, so after three rounds only (0, 0, 0) is left
         for ax in (1, 0, 2):

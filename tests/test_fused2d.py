@@ -138,11 +138,11 @@ def test_fused_wavelet_families(backend, biort, qshift):
 
 
 def test_fused_unsupported_falls_back_to_generic_kernels(backend):
-    """qshift_c has 16 taps (no fused instance), near_sym_b_bp is a 6-tuple biort, 24x24 is below the fused
+    """qshift_32 has 32 taps (no fused instance), near_sym_b_bp is a 6-tuple biort, 24x24 is below the fused
     minimum: the generic CUDA kernels must produce the result instead."""
     rs = np.random.RandomState(3)
     X = rs.rand(64, 64).astype(np.float32)
-    for biort, qshift in (("near_sym_b", "qshift_c"), ("near_sym_b_bp", "qshift_b_bp")):
+    for biort, qshift in (("near_sym_b", "qshift_32"), ("near_sym_b_bp", "qshift_b_bp")):
         xf = dtcwt_b200.Transform2d(biort, qshift)
         to = O.Transform2d(coeffs.biort(biort), coeffs.qshift(qshift))
         with Launches() as L:
@@ -154,6 +154,25 @@ def test_fused_unsupported_falls_back_to_generic_kernels(backend):
     with Launches() as L:
         dtcwt_b200.Transform2d("near_sym_b", "qshift_b").forward(X[:24, :24], 1)
     assert any("colfilter" in n for n in L.names)
+
+
+def test_fused_16_tap_qshift(backend):
+    """qshift_c: 16 taps, m / 2 even -- colifilt's second index scheme (reference lowlevel.py:205-231) -- runs on the
+    fused level kernels too."""
+    rs = np.random.RandomState(23)
+    X = rs.rand(2, 256, 264).astype(np.float32)          # level 3 works on 64 x 66 -> 32 x 33, still above the fused minimum
+    xf = dtcwt_b200.Transform2d("near_sym_b", "qshift_c")
+    to = O.Transform2d(coeffs.biort("near_sym_b"), coeffs.qshift("qshift_c"))
+    with Launches() as L:
+        p = xf.forward_channels(X, "nhw", 3)
+        Z = npy(xf.inverse_channels(p, "nhw"))
+    assert L.only_fused(), L.names
+    for i in range(2):
+        po = to.forward(X[i], 3)
+        assert rel_err(p.lowpass[i], po.lowpass) < REL_TOL
+        for a, b in zip(p.highpasses, po.highpasses):
+            assert rel_err(a[i], b) < REL_TOL
+    assert np.abs(Z - X).max() < 1e-5
 
 
 def test_fused_batch_and_generic_agree(backend):

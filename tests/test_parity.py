@@ -460,3 +460,54 @@ def test_fused3d_equals_per_axis_composition(backend):
     for a, b in zip(p.highpasses, q.highpasses):
         assert rel_err(a, b) < REL_TOL
     assert rel_err(Z, Zq) < REL_TOL
+
+
+def test_transform3d_even_length_biort(backend):
+    """Haar level-1 filters in 3-D (reference tests/test_xfm3.py:42-58; transform3d.py:223-251, 437-438): n+1 lowpass
+    samples per axis, highpasses at the original size, the inverse drops the first sample of every axis."""
+    h0 = np.array((1.0, 1.0))
+    g0 = h0 / h0.sum()
+    h0 = h0 / h0.sum()
+    h1 = g0 * np.cumprod(-np.ones_like(g0))
+    g1 = -h0 * np.cumprod(-np.ones_like(h0))
+    haar = tuple(np.asarray(h).reshape(-1, 1) for h in (h0, g0, h1, g1))
+    X = np.random.RandomState(21).rand(12, 16, 20)
+    xf = dtcwt_b200.Transform3d(haar, "qshift_a")
+    p = xf.forward(X, 1)
+    po = O.Transform3d(haar, coeffs.qshift("qshift_a")).forward(X, 1)
+    assert p.lowpass.shape == (13, 17, 21) and p.highpasses[0].shape == (6, 8, 10, 28)
+    assert rel_err(p.lowpass, po.lowpass) < 1e-12 and rel_err(p.highpasses[0], po.highpasses[0]) < 1e-12
+    Z = npy(xf.inverse(p))
+    assert Z.shape == X.shape and rel_err(Z, O.Transform3d(haar, coeffs.qshift("qshift_a")).inverse(po)) < 1e-12
+    # the reference's own test: an ellipsoid that vanishes at the borders is reconstructed exactly
+    g = np.arange(-16, 16) / 16.0
+    r = np.sqrt(g[:, None, None] ** 2 * 2 + g[None, :, None] ** 2 * 3 + g[None, None, :] ** 2 * 1.5)
+    E = np.where(r < 0.9, 1.0, 0.0)
+    Yl, Yh = dtcwt_b200.dtwavexfm3(E, 1, biort=haar)
+    assert np.abs(dtcwt_b200.dtwaveifm3(Yl, Yh, biort=haar) - E).max() < 1e-12
+    with pytest.raises(ValueError):
+        xf.forward(X, 1, discard_level_1=True)
+
+
+def test_compat_wrappers(backend):
+    """dtcwt.compat's MATLAB-style tuple API (reference compat.py:32-288) on this backend."""
+    rs = np.random.RandomState(17)
+    v = rs.rand(64, 3)
+    Yl, Yh, Ys = dtcwt_b200.dtwavexfm(v, 3, include_scale=True)
+    po = O.Transform1d(coeffs.biort("near_sym_a"), coeffs.qshift("qshift_a")).forward(v, 3, True)
+    assert rel_err(Yl, po.lowpass) < 1e-12 and len(Yh) == 3 and len(Ys) == 3
+    assert rel_err(dtcwt_b200.dtwaveifm(Yl, Yh), v) < 1e-10
+    X = rs.rand(48, 40).astype(np.float32)
+    Yl, Yh = dtcwt_b200.dtwavexfm2(X, 2, "near_sym_b", "qshift_b")
+    po = O.Transform2d(coeffs.biort("near_sym_b"), coeffs.qshift("qshift_b")).forward(X, 2)
+    assert isinstance(Yl, np.ndarray) and rel_err(Yl, po.lowpass) < REL_TOL and rel_err(Yh[1], po.highpasses[1]) < REL_TOL
+    Z = dtcwt_b200.dtwaveifm2(Yl, Yh, "near_sym_b", "qshift_b", gain_mask=np.ones((6, 2)))
+    assert isinstance(Z, np.ndarray) and np.abs(Z - X).max() < 1e-5
+    assert dtcwt_b200.dtwavexfm2b is dtcwt_b200.dtwavexfm2 and dtcwt_b200.dtwaveifm2b is dtcwt_b200.dtwaveifm2
+    Ylb, Yhb = dtcwt_b200.dtwavexfm2b(X, 2, "near_sym_b_bp", "qshift_b_bp")
+    pb = O.Transform2d(coeffs.biort("near_sym_b_bp"), coeffs.qshift("qshift_b_bp")).forward(X, 2)
+    assert rel_err(Yhb[0], pb.highpasses[0]) < REL_TOL and rel_err(Yhb[1], pb.highpasses[1]) < REL_TOL
+    V = rs.rand(16, 16, 16)
+    Yl, Yh = dtcwt_b200.dtwavexfm3(V, 2, ext_mode=4, discard_level_1=True)
+    assert Yh[0] is None and Yh[1].shape == (4, 4, 4, 28)
+    assert dtcwt_b200.dtwaveifm3(Yl, Yh).shape == V.shape
