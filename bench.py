@@ -67,9 +67,12 @@ def parse():
     ap.add_argument("--side", type=int, default=SIDE, help=argparse.SUPPRESS)   # debugging only
     ap.add_argument("--biort", default=BIORT, help="level-1 family (default: the north-star pair near_sym_b/qshift_b)")
     ap.add_argument("--qshift", default=QSHIFT)
-    ap.add_argument("--workload", default="2d", choices=["2d", "3d"],
-                    help="3d = BASELINE configs[3] (256^3 volumes, 3 levels, discard_level_1): informational line, "
-                         "runs on the generic CUDA kernels; the headline metric is the default 2d")
+    ap.add_argument("--workload", default="2d", choices=["2d", "3d", "reg"],
+                    help="2d (default) = the headline metric, BASELINE configs[2]; 3d = configs[3] (256^3 volumes, 3 levels, "
+                         "discard_level_1, fused 3-D levels), Mvoxels/s; reg = configs[4] (estimatereg on 1080p frame pairs), pairs/s")
+    ap.add_argument("--total-images", type=int, default=None,
+                    help="2d only: STRONG scaling -- the job is this many images in all (BASELINE configs[2]: 1024), "
+                         "total/world per rank in chunks of --images; overrides --steps")
     return ap.parse_args()
 
 
@@ -403,6 +406,13 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     assert _lib.lib().dtcwt_b200_is_device_build() == 1
+    scaling = "weak"
+    if args.total_images:
+        # the job as SURVEY 8(d)/(e) specify it: a fixed batch (1024 images) split into contiguous slices, one per
+        # rank (parallel.shard_range), each slice processed in chunks of --images: total work is fixed -> strong scaling
+        lo, hi = parallel.shard_range(args.total_images, rank, world)
+        steps = max(1, (parallel.shard_range(args.total_images, 0, world)[1]) // args.images)      # rank 0 owns the largest slice
+        scaling = "strong"
 
     # the one collective of the job: rank 0's filter taps to everyone (about 1 KB)
     biort = parallel.broadcast_taps(coeffs.biort(BIORT), 0, dev)
@@ -541,13 +551,17 @@ def run_ours(args):
     # ---------------------------------------------------------------- end-to-end from pinned host memory
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(torch, dist, xf, pool, steps, world, dev, barrier, nimg, side)
+        def fn(x):
+            return xf.inverse_channels(xf.forward_channels(x, "nhw", nlevels=NLEVELS), "nhw")
+        e2e = run_e2e_generic(torch, dist, fn, pool, steps, world, dev, barrier, (nimg, side, side), UNIT)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
-            "ms_per_step": round(ms_total / steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+            "ms_per_step": round(ms_total / steps, 4), "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args), **({"total_images": args.total_images,
+                                                                                      "images_per_rank": steps * nimg} if args.total_images else {})),
+            "clocks": clocks,
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
             "hbm_frac_of_measured_peak": round(ALGO_BYTES_PER_PIXEL * value * 1e6 / 1e9 / (peak * world), 4),
         }
@@ -555,59 +569,6 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def run_e2e(torch, dist, xf, pool, steps, world, dev, barrier, nimg, side):
-    """The same step through the public API starting from HOST memory: every step uploads its chunk
-    from pinned memory (H2D) and reads the reconstruction back (D2H); copies of step i+1 / i-1
-    overlap the kernels of step i on separate streams.  Timed with CUDA events, max over ranks."""
-    nbuf = 2
-    host_in = [torch.empty((nimg, side, side), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
-    host_out = [torch.empty((nimg, side, side), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
-    for b in range(nbuf):
-        host_in[b].copy_(pool[b % len(pool)].cpu())
-    dev_in = [torch.empty((nimg, side, side), dtype=torch.float32, device=dev) for _ in range(nbuf)]
-    dev_out = [torch.empty((nimg, side, side), dtype=torch.float32, device=dev) for _ in range(nbuf)]
-    compute = torch.cuda.current_stream()
-    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-    ev_in = [torch.cuda.Event() for _ in range(nbuf)]
-    ev_done = [torch.cuda.Event() for _ in range(nbuf)]
-    ev_out = [torch.cuda.Event() for _ in range(nbuf)]
-
-    def run(n):
-        for i in range(n):
-            b = i % nbuf
-            with torch.cuda.stream(s_in):
-                s_in.wait_event(ev_done[b])            # previous user of dev_in[b] has finished
-                dev_in[b].copy_(host_in[b], non_blocking=True)
-                ev_in[b].record(s_in)
-            compute.wait_event(ev_in[b])
-            compute.wait_event(ev_out[b])              # dev_out[b] has been drained
-            p = xf.forward_channels(dev_in[b], "nhw", nlevels=NLEVELS)
-            dev_out[b].copy_(xf.inverse_channels(p, "nhw"))
-            ev_done[b].record(compute)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_done[b])
-                host_out[b].copy_(dev_out[b], non_blocking=True)
-                ev_out[b].record(s_out)
-        s_out.synchronize()
-
-    run(2)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run(steps)
-    torch.cuda.synchronize()
-    e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    nbytes = nimg * side * side * 4
-    val = world * nimg * side * side * steps / (float(ms.item()) / 1e3) / 1e6
-    return {"value": round(val, 2), "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-            "note": "pinned host chunk -> forward_channels -> inverse_channels -> pinned host; copies overlap "
-                    "compute on side streams; PCIe-bound", "ms_per_step": round(float(ms.item()) / steps, 3)}
 
 
 _REAL_STDOUT = None
@@ -840,8 +801,8 @@ def run_3d(args):
 
     e2e = None
     if not args.no_e2e:
-        def fn(x, out):
-            out.copy_(xf.inverse(xf.forward_channels(x, nlevels=3, discard_level_1=True)))
+        def fn(x):
+            return xf.inverse(xf.forward_channels(x, nlevels=3, discard_level_1=True))
         e2e = run_e2e_generic(torch, dist, fn, pool, steps, world, dev, barrier, (nvol, side, side, side), "Mvoxels/s")
     if rank == 0:
         emit({"metric": METRIC_3D, "value": round(value, 2), "unit": "Mvoxels/s", "n_gpus": world, "steps": steps, "warmup": warm,
@@ -854,8 +815,10 @@ def run_3d(args):
 
 
 def run_e2e_generic(torch, dist, fn, pool, steps, world, dev, barrier, shape, unit, nbuf=3):
-    """End to end from pinned HOST memory: every step uploads its chunk (H2D), runs fn(dev_in, dev_out) and reads the
-    result back (D2H); `nbuf` chunks are in flight so the copies of neighbouring steps overlap the kernels."""
+    """End to end through the public API from pinned HOST memory: every step uploads its chunk (H2D), runs
+    res = fn(dev_in) and reads the result back (D2H) straight from the tensor the API returned; `nbuf` chunks are in
+    flight so the copies of neighbouring steps overlap the kernels on side streams.  Timed with CUDA events, max over
+    ranks.  The copy roofline of a step is bytes / the bidirectional pinned-copy bandwidth (tools/exp/copy_bw.py)."""
     numel = 1
     for v in shape:
         numel *= v
@@ -864,28 +827,30 @@ def run_e2e_generic(torch, dist, fn, pool, steps, world, dev, barrier, shape, un
     for b in range(nbuf):
         host_in[b].copy_(pool[b % len(pool)].cpu())
     dev_in = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(nbuf)]
-    dev_out = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(nbuf)]
     compute = torch.cuda.current_stream()
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
     ev_in = [torch.cuda.Event() for _ in range(nbuf)]
     ev_done = [torch.cuda.Event() for _ in range(nbuf)]
     ev_out = [torch.cuda.Event() for _ in range(nbuf)]
+    keep = [None] * nbuf
 
     def run(n):
         for i in range(n):
             b = i % nbuf
             with torch.cuda.stream(s_in):
-                s_in.wait_event(ev_done[b])
+                s_in.wait_event(ev_done[b])            # the previous user of dev_in[b] has finished
                 dev_in[b].copy_(host_in[b], non_blocking=True)
                 ev_in[b].record(s_in)
             compute.wait_event(ev_in[b])
-            compute.wait_event(ev_out[b])
-            fn(dev_in[b], dev_out[b])
+            res = fn(dev_in[b])
             ev_done[b].record(compute)
             with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_out[b])            # host_out[b] has been drained by its previous copy (stream order)
                 s_out.wait_event(ev_done[b])
-                host_out[b].copy_(dev_out[b], non_blocking=True)
+                host_out[b].copy_(res, non_blocking=True)
+                res.record_stream(s_out)
                 ev_out[b].record(s_out)
+            keep[b] = res
         s_out.synchronize()
 
     run(nbuf)
@@ -899,10 +864,170 @@ def run_e2e_generic(torch, dist, fn, pool, steps, world, dev, barrier, shape, un
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms.item()) / steps
     val = world * numel * steps / (float(ms.item()) / 1e3) / 1e6
-    return {"value": round(val, 2), "unit": unit, "h2d_bytes_per_step": numel * 4, "d2h_bytes_per_step": numel * 4,
-            "note": "pinned host chunk -> forward -> inverse -> pinned host; %d chunks in flight, copies on side streams" % nbuf,
-            "ms_per_step": round(float(ms.item()) / steps, 3)}
+    out = {"value": round(val, 2), "unit": unit, "h2d_bytes_per_step": numel * 4, "d2h_bytes_per_step": numel * 4,
+           "note": "pinned host chunk -> forward -> inverse -> pinned host through the public API; %d chunks in flight, copies on "
+                   "side streams, D2H straight from the returned tensor" % nbuf,
+           "ms_per_step": round(ms_step, 3)}
+    bw = copy_roofline_gbs(world)
+    if bw is not None:
+        ideal_ms = numel * 4 / (bw * 1e9) * 1e3
+        out["copy_roofline"] = {"bidir_gbs_per_gpu": bw, "ideal_ms_per_step": round(ideal_ms, 3), "frac": round(ideal_ms / ms_step, 4),
+                                "source": "profiles/r2_copy_bw.json (tools/exp/copy_bw.py on this pool, %d GPU(s) copying at once)" % world}
+    return out
+
+
+def copy_roofline_gbs(world):
+    """Measured pinned-memory copy bandwidth per GPU and direction with H2D and D2H running together on `world` GPUs of
+    one box (committed measurement, profiles/r2_copy_bw.json); None when there is no entry for this GPU count."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_copy_bw.json")) as f:
+            return float(json.load(f)[str(world)]["bidir_each_gbs_per_gpu_min"])
+    except Exception:
+        return None
+
+
+# =============================================================================== config 5: registration of frame pairs
+METRIC_REG = "frame pairs/s dtcwt.registration.estimatereg 1920x1080 5-level"
+
+
+def _reg_pair(shape, seed):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import reg_frames
+    f1, f2 = reg_frames(shape, seed)
+    return f1.astype("float32"), f2.astype("float32")
+
+
+def _cpu_worker_reg(job):
+    """Two 5-level forward transforms + estimatereg of one frame pair with the reference on one core."""
+    shape, seed, dump = job
+    for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[v] = "1"
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import logging
+    import refshim
+    logging.disable(logging.WARNING)
+    d, reg = refshim.load(), refshim.load_registration()
+    f1, f2 = _reg_pair(shape, seed)
+    xf = d.numpy.Transform2d()                                     # library defaults, as examples/register_images.py
+    t0 = time.perf_counter()
+    avecs = reg.estimatereg(xf.forward(f1, nlevels=5), xf.forward(f2, nlevels=5))      # dtcwt/registration.py:304
+    dt = time.perf_counter() - t0
+    if dump:
+        np.save(os.path.join(dump, "avecs.npy"), avecs)
+    return dt
+
+
+def run_reg(args):
+    """BASELINE configs[4]: estimatereg on batched 1080 x 1920 fp32 frame pairs, 5 levels, default wavelets.  A step =
+    forward transform of both frames of every pair of the chunk + estimatereg, all on the device."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import dtcwt_b200
+    from dtcwt_b200 import _lib, parallel, registration as R
+    steps = args.steps if args.steps is not None else 10
+    warm = max(3, args.warmup if args.warmup is not None else 3)
+    rank, world, local = parallel.init("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    npair = args.images if args.images != 16 else 32
+    shape = (1080, 1920)
+    xf = dtcwt_b200.Transform2d()
+    base1, base2 = _reg_pair(shape, 99)
+    g = torch.Generator(device=dev)
+    g.manual_seed(99 + rank)
+    # every pair of a chunk is the seeded pair plus its own low-amplitude noise: distinct data, same flow
+    pool = []
+    for c in range(3):
+        n1 = 0.01 * torch.rand((npair,) + shape, dtype=torch.float32, device=dev, generator=g)
+        pool.append((torch.from_numpy(base1).to(dev) + n1, torch.from_numpy(base2).to(dev) + n1))
+    pool[0][0][0].copy_(torch.from_numpy(base1))
+    pool[0][1][0].copy_(torch.from_numpy(base2))
+
+    def step(i):
+        a, b = pool[i % 3]
+        return R.estimatereg(xf.forward_channels(a, "nhw", nlevels=5), xf.forward_channels(b, "nhw", nlevels=5))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    parity, cpu_baseline = None, None
+    if rank == 0:
+        got = step(0)[0].cpu().numpy()
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import refshim
+        if world == 1 and not args.no_cpu_baseline and refshim.available():
+            import multiprocessing as mp
+            import shutil
+            import tempfile
+            cores = min(host_cores(), 64)
+            dump = tempfile.mkdtemp(prefix="dtcwt_benchreg_")
+            try:
+                jobs = [(shape, 99, dump if i == 0 else None) for i in range(cores)]
+                with mp.get_context("spawn").Pool(cores) as wp:
+                    wp.map(_cpu_worker_reg, [((135, 240), 1, None)] * cores)
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        wp.map(_cpu_worker_reg, jobs)
+                    wall = time.perf_counter() - t0
+                want = np.load(os.path.join(dump, "avecs.npy"))
+            finally:
+                shutil.rmtree(dump, ignore_errors=True)
+            err = np.abs(got - want)
+            cpu_baseline = {"value": round(3 * cores / wall, 3), "unit": "frame pairs/s", "cores": cores, "kind": "reference",
+                            "sample": "%d worker processes x 3 frame pairs each: two 5-level forward transforms + estimatereg with the "
+                                      "unmodified reference (oracle/_ref) (%.1f s wall)" % (cores, wall)}
+            parity = {"avecs_max_abs_err": float(err.max()), "avecs_median_abs_err": float(np.median(err)),
+                      "avecs_max_abs": float(np.abs(want).max()), "checked": "affine-parameter grid of pair 0 of chunk 0 vs the reference's "
+                      "estimatereg on the reference's own float32 pyramids", "tolerance": 1e-4, "ok": bool(err.max() < 1e-4)}
+    log = LaunchLog(torch)
+    _lib.set_launch_hook(log)
+    for i in range(warm):
+        step(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.prepare()
+        sampler.start()
+    log.count = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(steps):
+        step(warm + i)
+    e1.record()
+    barrier()
+    launches = log.count
+    _lib.set_launch_hook(None)
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * npair * steps / (ms_total / 1e3)
+    peak, peak_src = measured_peak_gbs()
+    # compulsory traffic of the two forward transforms (read 4 + write 16 B/pixel each); estimatereg works on levels 3-5 only
+    algo = 2 * 20.0 * npair * shape[0] * shape[1]
+    if rank == 0:
+        emit({"metric": METRIC_REG, "value": round(value, 2), "unit": "frame pairs/s", "n_gpus": world, "steps": steps, "warmup": warm,
+              "ms_per_step": round(ms_total / steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+              "dtype": "f32 transforms, f64 registration arithmetic", "data": "synthetic",
+              "config": {"workload": "estimatereg on chunks of %d frame pairs of 1080x1920 fp32, 5 levels, near_sym_a+qshift_a "
+                                     "(BASELINE configs[4]); both forward transforms are inside the step" % npair,
+                         "pairs_per_gpu_per_step": npair, "height": shape[0], "width": shape[1], "nlevels": 5},
+              "clocks": clocks, "gpu_launches": launches,
+              "roofline": {"bound": "hbm", "achieved": round(algo * steps / (ms_total / 1e3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                           "frac": round(algo * steps / (ms_total / 1e3) / 1e9 / peak, 4), "traffic": None, "peak_source": peak_src,
+                           "note": "whole step against the compulsory traffic of its two 5-level forward transforms (40 B per frame-pair pixel)"},
+              "cpu_baseline": cpu_baseline, "parity": parity})
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
@@ -924,6 +1049,9 @@ def main():
         sys.exit(subprocess.call(cmd))
     if args.workload == "3d":
         run_3d(args)
+        return
+    if args.workload == "reg":
+        run_reg(args)
         return
     run_ours(args)
 

@@ -104,10 +104,10 @@ typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps
 #endif
 typedef InvS1<19, 19, 0x7ffffu, 0x7ffffu, 24, 3> InvL1_19_19;       // any odd pair up to 19 taps (zero-padded)
 // the same with the inputs staged by bulk copies (ring, stages, prefetch depth); the default when rows are 16-byte aligned
-typedef InvS1T<19, 13, kMask19, kMask13, 24, 6, 4, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1> > InvT1_nsb;
-typedef InvS1T<19, 13, kMask19, kMask13, 24, 6, 5, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1> > InvT1_nsb5;   // experiment: DTCWT_B200_INV_DEPTH=5
-typedef InvS1T<19, 19, 0x7ffffu, 0x7ffffu, 24, 6, 4> InvT1_19_19;
-typedef InvS1T<7, 5, 0x7fu, 0x1fu, 8, 4, 3> InvT1_7_5;
+typedef InvS1T<19, 13, kMask19, kMask13, 24, 6, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1> > InvT1_nsb;
+typedef InvS1T<19, 13, kMask19, kMask13, 24, 4, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1> > InvT1_nsb4;   // experiment: DTCWT_B200_INV_NSTAGE=4
+typedef InvS1T<19, 19, 0x7ffffu, 0x7ffffu, 24, 6> InvT1_19_19;
+typedef InvS1T<7, 5, 0x7fu, 0x1fu, 8, 4> InvT1_7_5;
 typedef InvS1<7, 5, 0x7fu, 0x1fu, 8, 2> InvL1_7_5;                  // near_sym_a (+ legall 3/5)
 // levels >= 2: q-shift pairs; every shipped family has a positive lowpass and a negative highpass tap correlation
 template <int M> struct FwdLq { typedef Fwd2d<SpecDec<M, true>, SpecDec<M, false>, 32, 16, 4> type; };
@@ -339,7 +339,7 @@ int dtcwt_b200_inv2d_level1_f32(const float* z, const float* yh, float* out, int
     }
     if (staged && K1 == 13 && BakedTaps<NearSymB_g0>::same(a.g0) && BakedTaps<NearSymB_g1>::same(a.g1)) {
         a.periods = choose_periods(a.rows, InvT1_nsb::RING, (int64_t)InvT1_nsb::tiles_c(a) * a.n);
-        if (env_int("DTCWT_B200_INV_DEPTH", 4) == 5) return launch_invs1t<InvT1_nsb5>(a, stream);
+        if (env_int("DTCWT_B200_INV_NSTAGE", 6) == 4) return launch_invs1t<InvT1_nsb4>(a, stream);
         return launch_invs1t<InvT1_nsb>(a, stream);
     }
     if (staged) {

@@ -107,8 +107,10 @@ __global__ void __launch_bounds__(kStreamThreads, K::kMinBlocks) invs1_kernel(co
 }
 
 // streaming level-1 inverse with bulk-copy staged inputs (stream2d.cuh: InvS1T)
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kStreamThreads) : "memory"); }
+
 template <class K>
-__global__ void __launch_bounds__(kStreamThreads, K::kMinBlocks) invs1t_kernel(const __grid_constant__ typename K::Args a) {
+__global__ void __launch_bounds__(K::kLaunchThreads, K::kMinBlocks) invs1t_kernel(const __grid_constant__ typename K::Args a) {
     __shared__ __align__(8) Mbar full[K::NSTAGE], empty[K::NSTAGE];
     const int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z, tid = threadIdx.x;
     if (tid == 0) {
@@ -123,15 +125,22 @@ __global__ void __launch_bounds__(kStreamThreads, K::kMinBlocks) invs1t_kernel(c
     typename K::Pipe pipe;
     pipe.full = full;
     pipe.empty = empty;
+    if (tid >= kStreamThreads) {                 // producer warp: one lane walks over the steps of the run, as far ahead as the ring allows
+        if (tid == kStreamThreads) {
+            const int total = K::total_steps(a, by);
+            for (int g = 0; g < total; ++g) K::produce(a, fused_smem, pipe, bx, by, bz, g);
+        }
+        return;
+    }
     typename K::Thread th;
     K::init(a, th, fused_smem, pipe, bx, by, bz, tid);
     const int np = K::run_periods(a, by);
     for (int p = 0; p < np; ++p) {
         K::cols(a, th, fused_smem, pipe, bx, by, bz, tid, p);
         if (p > 0) {
-            __syncthreads();
+            consumer_barrier();                  // the eight consumer warps only (named barrier 1)
             K::rows(a, fused_smem, bx, by, bz, tid, p);
-            __syncthreads();
+            consumer_barrier();
         }
     }
 }
@@ -296,7 +305,7 @@ static int launch_invs1t(typename K::Args& a, void* stream) {
     if (a.n == 0) return DTCWT_B200_OK;
     if (K::tiles_r(a) > 65535 || a.n > 65535) return DTCWT_B200_EUNSUPPORTED;      // grid.y / grid.z limits
     const dim3 grid((unsigned)K::tiles_c(a), (unsigned)K::tiles_r(a), (unsigned)a.n);
-    invs1t_kernel<K><<<grid, kStreamThreads, smem, (cudaStream_t)stream>>>(a);
+    invs1t_kernel<K><<<grid, K::kLaunchThreads, smem, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
 

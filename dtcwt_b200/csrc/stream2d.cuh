@@ -293,18 +293,21 @@ struct InvS1 {
 
 // =============================================================================== inverse level 1, staged inputs
 // InvS1 with its eight input streams (two lowpass rows, six sub-band rows per quad row) staged in shared memory by
-// asynchronous bulk copies (cp.async.bulk, the TMA unit) instead of per-thread global loads: one elected thread per
-// step issues the eight 1 KB row segments of the quad row DEPTH steps ahead into a ring of NSTAGE stages; a `full`
-// mbarrier per stage counts the bytes as they land, an `empty` one the consumers that have taken their four values.
-// The column-pass warps never wait on a global load, DEPTH x 8 KB per CTA are in flight whatever the register
-// budget, and the prefetch registers of InvS1 are gone.  Segments are 16-byte aligned because CQ is a multiple of 4
+// asynchronous bulk copies (cp.async.bulk, the TMA unit) instead of per-thread global loads: a ninth, PRODUCER warp
+// issues the eight 1 KB row segments of every quad row into a ring of NSTAGE stages and runs as far ahead as the ring
+// allows; a `full` mbarrier per stage counts the bytes as they land, an `empty` one the consumer warps that have taken
+// their four values.  The eight column-pass warps never wait on a global load, up to NSTAGE x 8 KB per CTA are in
+// flight whatever the register budget, and the prefetch registers of InvS1 are gone.  (A first version let consumer
+// threads issue the copies in turn: the address arithmetic of one lane then sat on the critical path of all eight
+// warps, which the ring couples to within NSTAGE - DEPTH steps of each other -- 2.2 ms instead of 1.2, profiles/r2.)  Segments are 16-byte aligned because CQ is a multiple of 4
 // (the strip's first quad column is even); on the left / right image border only the part of the segment that lies
 // inside the image is copied and the threads read their mirrored quad column (index th.idx) with the two columns
 // exchanged, exactly as InvS1 does.  The host falls back to InvS1 when rows are not 16-byte aligned.
-template <int K0, int K1, uint32_t M0, uint32_t M1, int RING_, int NSTAGE_, int DEPTH_, class T0 = ArgTaps, class T1 = ArgTaps>
+template <int K0, int K1, uint32_t M0, uint32_t M1, int RING_, int NSTAGE_, class T0 = ArgTaps, class T1 = ArgTaps>
 struct InvS1T {
     typedef InvS1Args Args;
-    static constexpr int RING = RING_, PER = RING_ / 2, NSTAGE = NSTAGE_, DEPTH = DEPTH_;
+    static constexpr int RING = RING_, PER = RING_ / 2, NSTAGE = NSTAGE_;
+    static constexpr int kLaunchThreads = kStreamThreads + 32;        // eight consumer warps + the producer warp
     static constexpr int C0 = (K0 - 1) / 2, C1 = (K1 - 1) / 2, CQ = round_up(C0, 4);
     static constexpr int kThreads = kStreamThreads;
     static constexpr int QC = kThreads / 2;
@@ -320,7 +323,7 @@ struct InvS1T {
     static constexpr int kSmemFloats = kYFloats + NSTAGE * kStageFloats;
     static constexpr int kMinBlocks = 2;
     static_assert(K0 >= K1 && (K0 & 1) && (K1 & 1) && K0 <= kStreamMaxTaps && (M0 & 1u), "filter pair");
-    static_assert(RING >= CQ + C0 + 1 && (RING % 2) == 0 && (PER % NSTAGE) == 0 && DEPTH >= 1 && DEPTH < NSTAGE, "ring / pipeline");
+    static_assert(RING >= CQ + C0 + 1 && (RING % 2) == 0 && (PER % NSTAGE) == 0 && NSTAGE >= 2, "ring / pipeline");
     static_assert(8 * (NSEG - 1) + WE0 <= CY && 8 * (NSEG - 1) + WE1 <= CY, "row-pass window inside the smem row");
     static_assert((kYFloats % 4) == 0 && (TWI % 4) == 0 && (CQ % 4) == 0, "16-byte aligned stages and segments");
 
@@ -348,12 +351,9 @@ struct InvS1T {
     static DTCWT_HD bool col_edge(const Args& a, int bx) { return (TWI * bx - CQ < 0) || (TWI * bx - CQ + CY > a.cols); }
     static DTCWT_HD int first_quad(int bx) { return (TWI * bx - CQ) / 2; }        // exact: both even; may be negative
 
-    // ONE thread: issue the eight row segments of step g (quad row quad_base(by, 0) + g, folded into the image)
-#ifdef DTCWT_EMU
-    static void produce(const Args& a, float* sm, const Pipe& pipe, int bx, int by, int bz, int g) {
-#else
-    static __device__ __noinline__ void produce(const Args& a, float* sm, const Pipe& pipe, int bx, int by, int bz, int g) {
-#endif
+    // ONE thread (lane 0 of the producer warp): issue the eight row segments of step g (quad row quad_base(by, 0) + g,
+    // folded into the image) once every consumer warp has released the stage's previous content
+    static DTCWT_D void produce(const Args& a, float* sm, const Pipe& pipe, int bx, int by, int bz, int g) {
         const int stage = g % NSTAGE;
         bool f;
         const int q = fold_quad(quad_base(a, by, 0) + g, a.rows / 2, f);
@@ -388,11 +388,8 @@ struct InvS1T {
         th.idx = gj - g0;
 #pragma unroll
         for (int i = 0; i < RING; ++i) th.acc[i] = zero2();
-        if (tid == 0) {
-            const int total = run_periods(a, by) * PER;
-            for (int g = 0; g < DEPTH && g < total; ++g) produce(a, sm, pipe, bx, by, bz, g);
-        }
     }
+    static DTCWT_HD int total_steps(const Args& a, int by) { return run_periods(a, by) * PER; }
 
     static DTCWT_D void c2q_rows(const F2 w0, const F2 w1, float g0, float g1, F2& top, F2& bot) {
         const float r0 = w0.x * g0, i0 = w0.y * g0;
@@ -410,8 +407,6 @@ struct InvS1T {
                                   const int u, bool cedge) {
         const int g = p * PER + u;
         const int stage = u % NSTAGE;                              // PER is a multiple of NSTAGE
-        const int total = run_periods(a, by) * PER;
-        if (tid == 32 * (u % (kThreads / 32)) && g + DEPTH < total) produce(a, sm, pipe, bx, by, bz, g + DEPTH);
         mbar_wait(&pipe.full[stage], (uint32_t)(g / NSTAGE) & 1u);
         const float* st = sm + kYFloats + stage * kStageFloats + (4 * ROLE) * kStreamFloats + 2 * th.idx;
         Raw cur;

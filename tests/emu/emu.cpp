@@ -103,9 +103,10 @@ static int launch_invs1(typename K::Args& a, void* /*stream*/) {
     return DTCWT_B200_OK;
 }
 
-// Staged streaming kernel: the device issues the bulk copies of step g + DEPTH from inside step g; here every step of a
-// period is run for all threads in turn, so a stage is always filled (by that step's issuer thread) DEPTH steps before
-// it is read and never while another thread of the same step reads it (DEPTH < NSTAGE).
+// Staged streaming kernel: on the device a producer warp fills the ring as far ahead as the empty barriers allow.  Here
+// every step of a period is run for all threads in turn and the producer is replayed at its MAXIMUM run-ahead: before
+// step g it fills step g + NSTAGE - 1, whose stage was last read in step g - 1 (complete), so every stage index and
+// the wrap of the ring are exercised exactly as on the device.
 template <class K>
 static int launch_invs1t(typename K::Args& a, void* /*stream*/) {
     std::vector<float> sm(K::kSmemFloats);
@@ -118,10 +119,14 @@ static int launch_invs1t(typename K::Args& a, void* /*stream*/) {
             for (int bx = 0; bx < K::tiles_c(a); ++bx) {
                 for (size_t i = 0; i < sm.size(); ++i) sm[i] = NAN;
                 for (int tid = 0; tid < K::kThreads; ++tid) K::init(a, th[tid], sm.data(), pipe, bx, by, bz, tid);
-                const int np = K::run_periods(a, by);
+                const int np = K::run_periods(a, by), total = K::total_steps(a, by);
+                for (int g = 0; g < K::NSTAGE - 1 && g < total; ++g) K::produce(a, sm.data(), pipe, bx, by, bz, g);
                 for (int p = 0; p < np; ++p) {
-                    for (int u = 0; u < K::PER; ++u)
+                    for (int u = 0; u < K::PER; ++u) {
+                        const int g = p * K::PER + u + K::NSTAGE - 1;
+                        if (g < total) K::produce(a, sm.data(), pipe, bx, by, bz, g);
                         for (int tid = 0; tid < K::kThreads; ++tid) K::step(a, th[tid], sm.data(), pipe, bx, by, bz, tid, p, u);
+                    }
                     if (p > 0)
                         for (int tid = 0; tid < K::kThreads; ++tid) K::rows(a, sm.data(), bx, by, bz, tid, p);
                 }

@@ -1,7 +1,7 @@
 # round 2, call E: staged level-1 inverse after the one-arrival-per-warp fix (depth 4 and 5) vs per-thread loads; ncu of the staged kernel
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -4
-for cfg in "DTCWT_B200_INV_STAGED=1" "DTCWT_B200_INV_STAGED=1 DTCWT_B200_INV_DEPTH=5" "DTCWT_B200_INV_STAGED=0"; do
+for cfg in "DTCWT_B200_INV_STAGED=1" "DTCWT_B200_INV_STAGED=1 DTCWT_B200_INV_NSTAGE=4" "DTCWT_B200_INV_STAGED=0"; do
   env $cfg timeout 600 python bench.py --no-cpu-baseline --no-e2e --steps 20 > gpurun_out/bench_r2e.json 2> gpurun_out/bench_r2e.err
   python - <<PY
 import json
