@@ -103,7 +103,7 @@ typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps
 typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 2, 2> InvL1_nsbC;   // arithmetic only
 #endif
 typedef InvS1<19, 19, 0x7ffffu, 0x7ffffu, 24, 3> InvL1_19_19;       // any odd pair up to 19 taps (zero-padded)
-// the same with the inputs staged by bulk copies (ring, stages, prefetch depth); the default when rows are 16-byte aligned
+// the same with the inputs staged by bulk copies (ring, stages); opt-in (DTCWT_B200_INV_STAGED=1), see dtcwt_b200_inv2d_level1_f32
 typedef InvS1T<19, 13, kMask19, kMask13, 24, 6, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1> > InvT1_nsb;
 typedef InvS1T<19, 13, kMask19, kMask13, 24, 4, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1> > InvT1_nsb4;   // experiment: DTCWT_B200_INV_NSTAGE=4
 typedef InvS1T<19, 19, 0x7ffffu, 0x7ffffu, 24, 6> InvT1_19_19;
@@ -330,8 +330,9 @@ int dtcwt_b200_inv2d_level1_f32(const float* z, const float* yh, float* out, int
     const uint32_t nz1 = taps_col_s(a.g1, g1o, m1, K1, 1.0);
     pair_tab(a.p0, a.g0, K0);
     pair_tab(a.p1, a.g1, K1);
-    // inputs staged by asynchronous bulk copies when every row segment is 16-byte aligned (DTCWT_B200_INV_STAGED=0: per-thread loads)
-    const bool staged = env_int("DTCWT_B200_INV_STAGED", 1) != 0 && (cols % 4) == 0 && (zs_row % 2) == 0 && (zs_band % 2) == 0 &&
+    // DTCWT_B200_INV_STAGED=1: inputs staged by asynchronous bulk copies (needs 16-byte aligned row segments).  Parity-tested,
+    // but measured SLOWER than the per-thread loads (1.35 vs 1.20 ms per 16 x 4096^2, profiles/r2_02): opt-in.
+    const bool staged = env_int("DTCWT_B200_INV_STAGED", 0) != 0 && (cols % 4) == 0 && (zs_row % 2) == 0 && (zs_band % 2) == 0 &&
                         (zs_n % 2) == 0 && aligned_to(z, 16) && aligned_to(yh, 16);
     if (staged && small) {
         a.periods = choose_periods(a.rows, InvT1_7_5::RING, (int64_t)InvT1_7_5::tiles_c(a) * a.n);

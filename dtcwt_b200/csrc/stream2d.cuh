@@ -351,29 +351,51 @@ struct InvS1T {
     static DTCWT_HD bool col_edge(const Args& a, int bx) { return (TWI * bx - CQ < 0) || (TWI * bx - CQ + CY > a.cols); }
     static DTCWT_HD int first_quad(int bx) { return (TWI * bx - CQ) / 2; }        // exact: both even; may be negative
 
-    // ONE thread (lane 0 of the producer warp): issue the eight row segments of step g (quad row quad_base(by, 0) + g,
-    // folded into the image) once every consumer warp has released the stage's previous content
-    static DTCWT_D void produce(const Args& a, float* sm, const Pipe& pipe, int bx, int by, int bz, int g) {
-        const int stage = g % NSTAGE;
-        bool f;
-        const int q = fold_quad(quad_base(a, by, 0) + g, a.rows / 2, f);
+    // Producer warp, lanes 0..7: lane i owns input stream i (0, 1: the two lowpass rows of a quad row; 2..7: sub-bands 0, 5,
+    // 2, 3, 1, 4).  Everything that does not change along the run -- the clipped segment, its first byte in quad row 0,
+    // the row pitch, the slot inside a stage -- is set up once, so a step costs a fold, one multiply-add and one copy.
+    struct Stream {
+        const float* base;         // first float of the (clipped) segment in quad row 0
+        int64_t pitch;             // floats per quad row
+        int dst;                   // float offset of the segment inside a stage
+        uint32_t bytes;
+    };
+    static DTCWT_D void stream_setup(const Args& a, Stream& s, int bx, int bz, int i) {
         const int g0 = first_quad(bx), nq = a.cols / 2;
         const int s0 = g0 < 0 ? 0 : g0;
         const int s1 = (g0 + QC < nq) ? g0 + QC : nq;
-        const uint32_t bytes = (uint32_t)(s1 - s0) * 8u;
-        if (g >= NSTAGE) mbar_wait(&pipe.empty[stage], (uint32_t)((g / NSTAGE) - 1) & 1u);     // every consumer has taken the stage's previous content
-        mbar_expect_tx(&pipe.full[stage], 8u * bytes);
-        float* st = sm + kYFloats + stage * kStageFloats + 2 * (s0 - g0);
-        const float* zrow = a.z + ((int64_t)bz * a.rows + 2 * q) * a.cols + 2 * s0;
-        bulk_copy(st, zrow, bytes, &pipe.full[stage]);
-        bulk_copy(st + kStreamFloats, zrow + a.cols, bytes, &pipe.full[stage]);
-        const float* yb = a.yh + 2 * ((int64_t)bz * a.zs_n + (int64_t)q * a.zs_row + s0);
-        bulk_copy(st + 2 * kStreamFloats, yb, bytes, &pipe.full[stage]);
-        bulk_copy(st + 3 * kStreamFloats, yb + 2 * 5 * a.zs_band, bytes, &pipe.full[stage]);
-        bulk_copy(st + 4 * kStreamFloats, yb + 2 * 2 * a.zs_band, bytes, &pipe.full[stage]);
-        bulk_copy(st + 5 * kStreamFloats, yb + 2 * 3 * a.zs_band, bytes, &pipe.full[stage]);
-        bulk_copy(st + 6 * kStreamFloats, yb + 2 * 1 * a.zs_band, bytes, &pipe.full[stage]);
-        bulk_copy(st + 7 * kStreamFloats, yb + 2 * 4 * a.zs_band, bytes, &pipe.full[stage]);
+        s.bytes = (uint32_t)(s1 - s0) * 8u;
+        s.dst = i * kStreamFloats + 2 * (s0 - g0);
+        if (i < 2) {
+            s.base = a.z + (int64_t)bz * a.rows * a.cols + (int64_t)i * a.cols + 2 * s0;
+            s.pitch = 2 * (int64_t)a.cols;
+        } else {
+            const int band = (i == 2) ? 0 : (i == 3) ? 5 : (i == 4) ? 2 : (i == 5) ? 3 : (i == 6) ? 1 : 4;
+            s.base = a.yh + 2 * ((int64_t)bz * a.zs_n + (int64_t)band * a.zs_band + s0);
+            s.pitch = 2 * a.zs_row;
+        }
+    }
+    // lane 0, before the copies of step g: every consumer warp has released the stage's previous content
+    static DTCWT_D void step_begin(const Stream& s, const Pipe& pipe, int g) {
+        const int stage = g % NSTAGE;
+        if (g >= NSTAGE) mbar_wait(&pipe.empty[stage], (uint32_t)((g / NSTAGE) - 1) & 1u);
+        mbar_expect_tx(&pipe.full[stage], 8u * s.bytes);
+    }
+    // lane i: the row segment of stream i for step g (quad row quad_base(by, 0) + g, folded into the image)
+    static DTCWT_D void step_copy(const Args& a, const Stream& s, float* sm, const Pipe& pipe, int by, int g) {
+        const int stage = g % NSTAGE;
+        bool f;
+        const int q = fold_quad(quad_base(a, by, 0) + g, a.rows / 2, f);
+        bulk_copy(sm + kYFloats + stage * kStageFloats + s.dst, s.base + (int64_t)q * s.pitch, s.bytes, &pipe.full[stage]);
+    }
+    // all eight streams of step g by one thread (host emulator)
+    static DTCWT_D void produce(const Args& a, float* sm, const Pipe& pipe, int bx, int by, int bz, int g) {
+        for (int i = 0; i < 8; ++i) {
+            Stream s;
+            stream_setup(a, s, bx, bz, i);
+            if (i == 0) step_begin(s, pipe, g);
+            step_copy(a, s, sm, pipe, by, g);
+        }
     }
 
     static DTCWT_D void init(const Args& a, Thread& th, float* sm, const Pipe& pipe, int bx, int by, int bz, int tid) {
