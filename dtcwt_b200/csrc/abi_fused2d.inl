@@ -90,6 +90,8 @@ constexpr uint32_t kMask19 = 0x7ffffu & ~(1u << 1) & ~(1u << 17);    // near_sym
 constexpr uint32_t kMask13 = 0x1fffu & ~(1u << 1) & ~(1u << 11);
 typedef Fwd2d<SpecCol<13, kMask13>, SpecCol<19, kMask19>, 64, 64, 8, BakedPhase<NearSymB_h0>, BakedPhase<NearSymB_h1s>,
               BakedPhase<NearSymB_h1> > FwdT1_nsb;    // near_sym_b: exact-zero taps compiled out, column taps as immediates
+typedef Fwd2d<SpecCol<13, kMask13>, SpecCol<19, kMask19>, 64, 64, 8, BakedPhase<NearSymB_h0>, BakedPhase<NearSymB_h1s>,
+              BakedPhase<NearSymB_h1>, kFwdSym> FwdT1_nsb_sym;    // the same, column pass with shared symmetric sums (DTCWT_B200_FWD_SYM=1)
 typedef Fwd2d<SpecCol<5>, SpecCol<7>, 64, 64, 8> FwdT1_5_7;                         // near_sym_a (+ legall 5/3)
 typedef Fwd2d<SpecCol<19>, SpecCol<19>, 64, 64, 8> FwdT1_19_19;                     // any odd pair up to 19 taps
 // level-1 forward: streaming kernels, selected with DTCWT_B200_FWD_STREAM=1 (h0 taps, h1 taps, masks of taps that may be non-zero, ring)
@@ -207,6 +209,7 @@ int dtcwt_b200_fwd2d_level1_f32(const float* x, float* lolo, float* yh, int64_t 
         pair_tab(c.ph0, r0, KT0);
         pair_tab(c.ph1s, t1s, K1);
         if (small) return launch_fwd2d<FwdT1_5_7>(c, stream);
+        if (nsb && env_int("DTCWT_B200_FWD_SYM", 0)) return launch_fwd2d<FwdT1_nsb_sym>(c, stream);     // the baked tables are symmetric
         if (nsb) return launch_fwd2d<FwdT1_nsb>(c, stream);
         return launch_fwd2d<FwdT1_19_19>(c, stream);
     }

@@ -67,6 +67,22 @@ DTCWT_D F2 fma2(const float c, const F2 v, const F2 acc) {
 #endif
 }
 
+// a + b on a pair of floats (PTX add.rn.f32x2, SASS FADD2)
+DTCWT_D F2 add2(const F2 a, const F2 b) {
+#ifdef DTCWT_EMU
+    F2 r;
+    r.x = a.x + b.x;
+    r.y = a.y + b.y;
+    return r;
+#else
+    F2 r;
+    asm("add.rn.f32x2 %0, %1, %2;"
+        : "=l"(reinterpret_cast<unsigned long long&>(r))
+        : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+    return r;
+#endif
+}
+
 DTCWT_HD constexpr int cmax(int a, int b) { return a > b ? a : b; }
 DTCWT_HD constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
@@ -210,7 +226,11 @@ struct Fwd2dArgs {
 //             s0 = V:h0 H:h0, s1 = V:h1 H:h0, s2 = V:h0 H:h1, s3 = V:h1 H:h1, image s at lolo + s * zs_band (floats);
 //             the host passes unscaled taps (the packers' scale belongs to cube2c, fused3d.cuh)
 //   kFwdLow   (3-D level 1 without highpasses, transform3d.py:291-315, 442-456)  V:h0 H:h0 only
-constexpr int kFwdQ2c = 0, kFwdRaw = 1, kFwdLow = 2;
+//   kFwdSym   kFwdQ2c for a level-1 pair whose two filters are SYMMETRIC (t[k] = t[K-1-k], all shipped biorthogonal
+//             families): the column pass gathers instead of scattering and forms the sums x[c-k] + x[c+k] once for BOTH
+//             filters, 8 FADD2 + 15 FFMA2 per output row pair instead of 28 FFMA2 for near_sym_b (the host checks the
+//             symmetry of the taps it is given bit for bit)
+constexpr int kFwdQ2c = 0, kFwdRaw = 1, kFwdLow = 2, kFwdSym = 3;
 
 template <class H0, class H1, int GH_, int GW_, int NGV_, class TV0 = RtPhase, class TV1S = RtPhase, class TV1 = RtPhase,
           int MODE_ = kFwdQ2c>
@@ -491,8 +511,84 @@ struct Fwd2d {
         }
     }
 
+    // kFwdSym: one output row pair of BOTH symmetric filters from the register window w (centre row c): the sums
+    // w[c-k] + w[c+k] are shared; taps known to be zero (MASK) are compiled out, sums nobody needs are never formed
+    template <class TLO, class THI>
+    static DTCWT_D void sym_row(const F2 (&w)[NR], const int c, const PhaseTaps& tlo, const PhaseTaps& thi, F2& lo, F2& hi) {
+        constexpr int C0 = (H0::K - 1) / 2, C1 = (H1::K - 1) / 2;
+        lo = fma2(TLO::get(tlo, 0, C0), w[c], zero2());
+        hi = fma2(THI::get(thi, 0, C1), w[c], zero2());
+#pragma unroll
+        for (int k = 1; k <= cmax(C0, C1); ++k) {
+            const bool ul = k <= C0 && H0::on(0, C0 + k), uh = k <= C1 && H1::on(0, C1 + k);
+            if (ul || uh) {
+                const F2 s = add2(w[c - k], w[c + k]);
+                if (ul) lo = fma2(TLO::get(tlo, 0, C0 + k), s, lo);
+                if (uh) hi = fma2(THI::get(thi, 0, C1 + k), s, hi);
+            }
+        }
+    }
+
+    template <class HH = H0>
+    static DTCWT_D typename std::enable_if<HH::P == 1 && HH::Q == 1>::type phase_cols_sym(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        const float* As = sm + RX * CX;
+        const float* Bs = As + RX * CA;
+        constexpr int NCP = GW / 2;
+        static_assert(HL == HR && NR == NGV + 2 * HL && (NGV % 2) == 0, "centred window");
+        for (int task = tid; task < NCP * (GH / NGV); task += kThreads) {
+            const int strip = task / NCP, cp = task - strip * NCP;
+            const int lrow = NGV * strip;
+            const int orow = GH * by + NGV * strip;
+            const int ocol = GW * bx + 2 * cp;
+            const int nrow = (ocol < a.out_cols) ? a.out_rows - orow : 0;
+            const int nq = nrow / 2;
+            float* zb = a.yh + 2 * ((int64_t)bz * a.zs_n + (int64_t)(orow / 2) * a.zs_row + ocol / 2);
+            const int64_t bs = 2 * a.zs_band, rs = 2 * a.zs_row;
+            float* dst = a.lolo + ((int64_t)bz * a.out_rows + orow) * a.out_cols + ocol;
+            F2 w[NR];
+#pragma unroll
+            for (int j = 0; j < NR; ++j) w[j] = *reinterpret_cast<const F2*>(As + (lrow + j) * CA + 2 * cp);
+#pragma unroll
+            for (int q = 0; q < NGV / 2; ++q) {
+                F2 l0, h0, l1, h1;
+                sym_row<TV0, TV1S>(w, 2 * q + HL, a.v0, a.v1s, l0, h0);
+                sym_row<TV0, TV1S>(w, 2 * q + 1 + HL, a.v0, a.v1s, l1, h1);
+                if (2 * q < nrow) *reinterpret_cast<F2*>(dst + (int64_t)(2 * q) * a.out_cols) = l0;
+                if (2 * q + 1 < nrow) *reinterpret_cast<F2*>(dst + (int64_t)(2 * q + 1) * a.out_cols) = l1;
+                if (q < nq) store_quad(h0, h1, zb + q * rs, zb + 5 * bs + q * rs);               // bands 0, 5
+            }
+#pragma unroll
+            for (int j = 0; j < NR; ++j) w[j] = *reinterpret_cast<const F2*>(Bs + (lrow + j) * CA + 2 * cp);
+#pragma unroll
+            for (int q = 0; q < NGV / 2; ++q) {
+                F2 l0, h0, l1, h1;
+                sym_row<TV0, TV1>(w, 2 * q + HL, a.v0, a.v1, l0, h0);
+                sym_row<TV0, TV1>(w, 2 * q + 1 + HL, a.v0, a.v1, l1, h1);
+                if (q < nq) {
+                    store_quad(l0, l1, zb + 2 * bs + q * rs, zb + 3 * bs + q * rs);              // bands 2, 3
+                    store_quad(h0, h1, zb + 1 * bs + q * rs, zb + 4 * bs + q * rs);              // bands 1, 4
+                }
+            }
+        }
+    }
+    template <class HH = H0>
+    static DTCWT_D typename std::enable_if<!(HH::P == 1 && HH::Q == 1)>::type phase_cols_sym(const Args&, float*, int, int, int, int) {}
+
+    // q2c of one quad (rows e0 / e1, two columns) -> sub-bands z0, z1 (the 1/sqrt2 is in the taps)
+    static DTCWT_D void store_quad(const F2 e0, const F2 e1, float* z0, float* z1) {
+        F2 w0, w1;
+        w0.x = e0.x - e1.y; w0.y = e0.y + e1.x;
+        w1.x = e0.x + e1.y; w1.y = e0.y - e1.x;
+        *reinterpret_cast<F2*>(z0) = w0;
+        *reinterpret_cast<F2*>(z1) = w1;
+    }
+
     // phase 4: column pass, one task = 2 adjacent columns x NGV groups of rows; results leave from registers
     static DTCWT_D void phase_cols(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        if (MODE == kFwdSym) {
+            phase_cols_sym(a, sm, bx, by, bz, tid);
+            return;
+        }
         if (MODE != kFwdQ2c) {
             phase_cols_real(a, sm, bx, by, bz, tid);
             return;

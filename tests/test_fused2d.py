@@ -257,3 +257,22 @@ def test_staged_level1_inverse_matches(backend, monkeypatch):
         for i in range(shape[0]):
             po = to.forward(X[i], 1)
             assert rel_err(Z1[i], to.inverse(po, np.array([[1.0], [0.5], [2.0], [1.5], [0.25], [3.0]]))) < REL_TOL
+
+
+def test_symmetric_sum_column_pass_matches(backend, monkeypatch):
+    """Level-1 forward with the shared symmetric sums in the column pass (kFwdSym, DTCWT_B200_FWD_SYM=1): same results
+    as the scatter form to rounding, oracle parity at the stated tolerance; odd sizes and image borders included."""
+    rs = np.random.RandomState(43)
+    for shape in ((2, 96, 200), (1, 67, 131)):
+        X = rs.rand(*shape).astype(np.float32)
+        xf = dtcwt_b200.Transform2d("near_sym_b", "qshift_b")
+        monkeypatch.setenv("DTCWT_B200_FWD_SYM", "0")
+        p0 = xf.forward_channels(X, "nhw", 1)
+        monkeypatch.setenv("DTCWT_B200_FWD_SYM", "1")
+        p1 = xf.forward_channels(X, "nhw", 1)
+        monkeypatch.delenv("DTCWT_B200_FWD_SYM")
+        assert rel_err(p1.lowpass, p0.lowpass) < 1e-6 and rel_err(p1.highpasses[0], p0.highpasses[0]) < 1e-6
+        to = O.Transform2d(coeffs.biort("near_sym_b"), coeffs.qshift("qshift_b"))
+        for i in range(shape[0]):
+            po = to.forward(X[i], 1)
+            assert rel_err(p1.lowpass[i], po.lowpass) < REL_TOL and rel_err(p1.highpasses[0][i], po.highpasses[0]) < REL_TOL
