@@ -91,7 +91,9 @@ constexpr uint32_t kMask13 = 0x1fffu & ~(1u << 1) & ~(1u << 11);
 typedef Fwd2d<SpecCol<13, kMask13>, SpecCol<19, kMask19>, 64, 64, 8, BakedPhase<NearSymB_h0>, BakedPhase<NearSymB_h1s>,
               BakedPhase<NearSymB_h1> > FwdT1_nsb;    // near_sym_b: exact-zero taps compiled out, column taps as immediates
 typedef Fwd2d<SpecCol<13, kMask13>, SpecCol<19, kMask19>, 64, 64, 8, BakedPhase<NearSymB_h0>, BakedPhase<NearSymB_h1s>,
-              BakedPhase<NearSymB_h1>, kFwdSym> FwdT1_nsb_sym;    // the same, column pass with shared symmetric sums (DTCWT_B200_FWD_SYM=1)
+              BakedPhase<NearSymB_h1>, kFwdSym> FwdT1_nsb_sym;    // the same, column pass with shared symmetric sums: the default (measured 5 % faster)
+typedef Fwd2d<SpecCol<5>, SpecCol<7>, 64, 64, 8, RtPhase, RtPhase, RtPhase, kFwdSym> FwdT1_5_7_sym;
+typedef Fwd2d<SpecCol<19>, SpecCol<19>, 64, 64, 8, RtPhase, RtPhase, RtPhase, kFwdSym> FwdT1_19_19_sym;
 typedef Fwd2d<SpecCol<5>, SpecCol<7>, 64, 64, 8> FwdT1_5_7;                         // near_sym_a (+ legall 5/3)
 typedef Fwd2d<SpecCol<19>, SpecCol<19>, 64, 64, 8> FwdT1_19_19;                     // any odd pair up to 19 taps
 // level-1 forward: streaming kernels, selected with DTCWT_B200_FWD_STREAM=1 (h0 taps, h1 taps, masks of taps that may be non-zero, ring)
@@ -208,10 +210,14 @@ int dtcwt_b200_fwd2d_level1_f32(const float* x, float* lolo, float* yh, int64_t 
         taps_col_s(r0, h0o, m0, KT0, 1.0);
         pair_tab(c.ph0, r0, KT0);
         pair_tab(c.ph1s, t1s, K1);
-        if (small) return launch_fwd2d<FwdT1_5_7>(c, stream);
-        if (nsb && env_int("DTCWT_B200_FWD_SYM", 0)) return launch_fwd2d<FwdT1_nsb_sym>(c, stream);     // the baked tables are symmetric
-        if (nsb) return launch_fwd2d<FwdT1_nsb>(c, stream);
-        return launch_fwd2d<FwdT1_19_19>(c, stream);
+        // symmetric pairs (every shipped biorthogonal family) share the sums x[c-k] + x[c+k] between the two column filters;
+        // checked bit for bit on the taps as the kernels will see them (DTCWT_B200_FWD_SYM=0: scatter form)
+        bool sym = env_int("DTCWT_B200_FWD_SYM", 1) != 0;
+        for (int k = 0; k < KT0 && sym; ++k) sym = c.v0.t[0][k] == c.v0.t[0][KT0 - 1 - k];
+        for (int k = 0; k < K1 && sym; ++k) sym = c.v1.t[0][k] == c.v1.t[0][K1 - 1 - k] && c.v1s.t[0][k] == c.v1s.t[0][K1 - 1 - k];
+        if (small) return sym ? launch_fwd2d<FwdT1_5_7_sym>(c, stream) : launch_fwd2d<FwdT1_5_7>(c, stream);
+        if (nsb) return sym ? launch_fwd2d<FwdT1_nsb_sym>(c, stream) : launch_fwd2d<FwdT1_nsb>(c, stream);
+        return sym ? launch_fwd2d<FwdT1_19_19_sym>(c, stream) : launch_fwd2d<FwdT1_19_19>(c, stream);
     }
     if (small) {
         a.periods = choose_periods(a.Lr, FwdL1_5_7::RING, (int64_t)FwdL1_5_7::tiles_c(a) * a.n);
@@ -251,7 +257,13 @@ int dtcwt_b200_fwd2d_levelq_f32(const float* x, float* lolo, float* yh, int64_t 
         a.ph1s.p[k].y = (k < m) ? a.h1s.t[0][k] : 0.f;
     }
     if (m == 10) return launch_fwd2d<FwdLq<10>::type>(a, stream);
-    if (m == 14) return launch_fwd2d<FwdLq<14>::type>(a, stream);
+    if (m == 14) {
+        const int v = env_int("DTCWT_B200_FWDQ_VARIANT", 0);       // tile-shape experiments (profiles/r2_05)
+        if (v == 1) return launch_fwd2d<Fwd2d<SpecDec<14, true>, SpecDec<14, false>, 32, 16, 2> >(a, stream);
+        if (v == 2) return launch_fwd2d<Fwd2d<SpecDec<14, true>, SpecDec<14, false>, 16, 16, 4> >(a, stream);
+        if (v == 3) return launch_fwd2d<Fwd2d<SpecDec<14, true>, SpecDec<14, false>, 16, 16, 2> >(a, stream);
+        return launch_fwd2d<FwdLq<14>::type>(a, stream);
+    }
     if (m == 16) return launch_fwd2d<FwdLq<16>::type>(a, stream);
     return launch_fwd2d<FwdLq<18>::type>(a, stream);
 }

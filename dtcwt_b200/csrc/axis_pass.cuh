@@ -56,10 +56,14 @@ struct AxisPass {
 #pragma unroll
         for (int i = 0; i < NOUT; ++i) axis_zero(acc[i]);
         const int l0 = Q * NG * gb - HL;                     // logical index of window sample 0
+        // a window that lies inside the stored samples needs no symmetric extension: one add per sample instead of the
+        // modulo of reflect_any (the per-sample index arithmetic made these passes issue-bound, profiles/r2_04)
+        const int s0 = l0 - a.pad_lo;
+        const bool inside = s0 >= 0 && s0 + NR <= a.len;
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
             if (fir_row_used<F, NG, HL>(j)) {
-                const int s = unpad(reflect_any(l0 + j, a.L), a.pad_lo, a.len);
+                const int s = inside ? s0 + j : unpad(reflect_any(l0 + j, a.L), a.pad_lo, a.len);
                 const VT v = *reinterpret_cast<const VT*>(xo + (int64_t)s * a.inner);
 #pragma unroll
                 for (int ii = 0; ii < NG; ++ii) {

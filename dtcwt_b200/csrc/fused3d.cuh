@@ -75,9 +75,11 @@ struct Z3Fwd {
 #pragma unroll
         for (int i = 0; i < NOUT; ++i) { lo[0][i] = zero2(); lo[1][i] = zero2(); hi[0][i] = zero2(); hi[1][i] = zero2(); }
         const int l0 = Q * NG * gz - HL;
+        const int z0 = l0 - a.pad0;
+        const bool inside = z0 >= 0 && z0 + NR <= a.d0;          // no symmetric extension needed: skip reflect_any's modulo
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
-            const int z = unpad(reflect_any(l0 + j, a.L0), a.pad0, a.d0);
+            const int z = inside ? z0 + j : unpad(reflect_any(l0 + j, a.L0), a.pad0, a.d0);
             const float* p = src + (int64_t)z * plane;
             const F2 v0 = *reinterpret_cast<const F2*>(p);
             const F2 v1 = *reinterpret_cast<const F2*>(p + a.w);
