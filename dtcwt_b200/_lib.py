@@ -32,12 +32,14 @@ _TYPED = {
     "cube2c": [_P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _P],
     "c2cube": [_P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _P],
     "reg_qtilde": [_P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _P],
+    "kp_energy": [_P, _P, _L, _L, _L, _L, _L, _L, _L, _I, _D, _D, _D, _P],
     "sample": [_P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _I, _TAPS, _TAPS, _P],
 }
 _UNTYPED = {
     "reg_boxrescale": [_P, _P, _L, _L, _L, _L, _L, _I, _P],
     "reg_solve": [_P, _P, _L, _I, _P],
     "reg_coords": [_P, _P, _P, _L, _L, _L, _L, _L, _I, _P],
+    "kp_maxima": [_P, _P, _L, _L, _L, _D, _I, _P],
 }
 _F32_ONLY = {
     "fwd2d_level1": [_P, _P, _P, _L, _L, _L, _I, _I, _TAPS, _I, _TAPS, _I, _L, _L, _L, _P],

@@ -49,11 +49,46 @@ static int sample_impl(const T* im, T* out, const double* xs, const double* ys, 
     return launch_1d<SampleElem<T> >(a, stream);
 }
 
+template <typename T>
+static int kp_energy_impl(const T* yh, double* e, int64_t n, int64_t h, int64_t w, int64_t s_n, int64_t s_band, int64_t s_row,
+                          int64_t s_col, int method, double scale_gain, double beta, double kappa, void* stream) {
+    if (n < 0 || h < 1 || w < 1 || method < 0 || method > 2) return DTCWT_B200_EINVAL;
+    if (n == 0) return DTCWT_B200_OK;
+    if (!yh || !e) return DTCWT_B200_EINVAL;
+    KpEnergyArgs<T> a;
+    a.yh = yh; a.e = e; a.n = n; a.h = h; a.w = w; a.s_n = s_n; a.s_band = s_band; a.s_row = s_row; a.s_col = s_col;
+    a.method = method; a.scale_gain = scale_gain; a.beta = beta; a.kappa = kappa;
+    return launch_1d<KpEnergyElem<T> >(a, stream);
+}
+
 }  // namespace dtcwt
 
 using namespace dtcwt;
 
 extern "C" {
+
+// keypoint.py:143-156: keypoint energy of one level's six sub-bands; method 0 fauqueur (scale_gain = alpha**(scale+1),
+// beta), 1 bendale, 2 kingsbury (kappa).  e is [n][h][w] float64.
+int dtcwt_b200_kp_energy_f32(const float* yh, double* e, int64_t n, int64_t h, int64_t w, int64_t s_n, int64_t s_band,
+                             int64_t s_row, int64_t s_col, int method, double scale_gain, double beta, double kappa, void* stream) {
+    return kp_energy_impl<float>(yh, e, n, h, w, s_n, s_band, s_row, s_col, method, scale_gain, beta, kappa, stream);
+}
+int dtcwt_b200_kp_energy_f64(const double* yh, double* e, int64_t n, int64_t h, int64_t w, int64_t s_n, int64_t s_band,
+                             int64_t s_row, int64_t s_col, int method, double scale_gain, double beta, double kappa, void* stream) {
+    return kp_energy_impl<double>(yh, e, n, h, w, s_n, s_band, s_row, s_col, method, scale_gain, beta, kappa, stream);
+}
+
+// keypoint.py:201-260 (_kp_energy_maxima): out [n][h][w][4] = (1 if the pixel is a kept local maximum else 0, refined row,
+// refined column, energy); refine != 0 fits the quadratic patch and drops maxima that move by more than half a pixel.
+int dtcwt_b200_kp_maxima(const double* x, double* out, int64_t n, int64_t h, int64_t w, double threshold, int refine, void* stream) {
+    if (n < 0 || h < 1 || w < 1) return DTCWT_B200_EINVAL;
+    if (n == 0) return DTCWT_B200_OK;
+    if (!x || !out) return DTCWT_B200_EINVAL;
+    if (h > 0x3fffffff || w > 0x3fffffff) return DTCWT_B200_EUNSUPPORTED;
+    KpMaximaArgs a;
+    a.x = x; a.out = out; a.n = n; a.h = h; a.w = w; a.threshold = threshold; a.refine = refine;
+    return launch_1d<KpMaximaElem>(a, stream);
+}
 
 // registration.py:141-212 (qtildematrices) for ONE level: src / ref are the level's six complex sub-bands of the (warped)
 // source and of the reference image, element (b, band, i, j) at 2*(b*x_n + band*x_band + i*x_row + j*x_col).

@@ -44,6 +44,26 @@ struct AxisPass {
     }
     static DTCWT_HD int64_t total(const Args& a) { return a.outer * blocks_along(a) * (a.inner / V); }
 
+    template <bool INSIDE>
+    static DTCWT_D void accumulate(const Args& a, const float* xo, int l0, int s0, VT (&acc)[NOUT]) {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            if (fir_row_used<F, NG, HL>(j)) {
+                const int s = INSIDE ? s0 + j : unpad(reflect_any(l0 + j, a.L), a.pad_lo, a.len);
+                const VT v = *reinterpret_cast<const VT*>(xo + (int64_t)s * a.inner);
+#pragma unroll
+                for (int ii = 0; ii < NG; ++ii) {
+#pragma unroll
+                    for (int ph = 0; ph < P; ++ph) {
+                        const int num = j - HL - Q * ii - F::b(ph);
+                        if (num >= 0 && (num % F::S) == 0 && (num / F::S) < F::K && F::on(ph, num / F::S))
+                            acc[P * ii + ph] = axis_fma(a.t.t[ph][num / F::S], v, acc[P * ii + ph]);
+                    }
+                }
+            }
+        }
+    }
+
     static DTCWT_D void run(const Args& a, int64_t gid) {
         const int ip_n = a.inner / V;
         const int ip = (int)(gid % ip_n);
@@ -57,25 +77,11 @@ struct AxisPass {
         for (int i = 0; i < NOUT; ++i) axis_zero(acc[i]);
         const int l0 = Q * NG * gb - HL;                     // logical index of window sample 0
         // a window that lies inside the stored samples needs no symmetric extension: one add per sample instead of the
-        // modulo of reflect_any (the per-sample index arithmetic made these passes issue-bound, profiles/r2_04)
+        // modulo of reflect_any.  Two copies of the unrolled loop behind one (warp-uniform) branch -- a per-sample select
+        // still evaluates the modulo and measured SLOWER than the plain loop (profiles/r2_05).
         const int s0 = l0 - a.pad_lo;
-        const bool inside = s0 >= 0 && s0 + NR <= a.len;
-#pragma unroll
-        for (int j = 0; j < NR; ++j) {
-            if (fir_row_used<F, NG, HL>(j)) {
-                const int s = inside ? s0 + j : unpad(reflect_any(l0 + j, a.L), a.pad_lo, a.len);
-                const VT v = *reinterpret_cast<const VT*>(xo + (int64_t)s * a.inner);
-#pragma unroll
-                for (int ii = 0; ii < NG; ++ii) {
-#pragma unroll
-                    for (int ph = 0; ph < P; ++ph) {
-                        const int num = j - HL - Q * ii - F::b(ph);
-                        if (num >= 0 && (num % F::S) == 0 && (num / F::S) < F::K && F::on(ph, num / F::S))
-                            acc[P * ii + ph] = axis_fma(a.t.t[ph][num / F::S], v, acc[P * ii + ph]);
-                    }
-                }
-            }
-        }
+        if (s0 >= 0 && s0 + NR <= a.len) accumulate<true>(a, xo, l0, s0, acc);
+        else accumulate<false>(a, xo, l0, s0, acc);
         float* yo = a.y + o * (int64_t)a.Lout * a.inner + V * ip;
 #pragma unroll
         for (int i = 0; i < NOUT; ++i) {

@@ -6,6 +6,7 @@
 #include "fused2d.cuh"
 #include "fused3d.cuh"
 #include "registration.cuh"
+#include "keypoint.cuh"
 #include "axis_pass.cuh"
 
 namespace dtcwt {

@@ -830,7 +830,7 @@ struct Inv2d {
     // FFMA2 of a scalar sample with the tap pair (t[ph][k], t[ph+2][k]) advances both -- half the issue slots of the scalar
     // form below.  pe[g] = outputs (0, 2), po[g] = outputs (1, 3) of group g.
     template <class GG = G0>
-    static DTCWT_D typename std::enable_if<GG::P == 4 && GG::Q == 2>::type rows_packed(const Args& a, const float* y1, const float* y2,
+    static DTCWT_D typename std::enable_if<GG::P == 4 && GG::Q == 2 && (GG::K & 1)>::type rows_packed(const Args& a, const float* y1, const float* y2,
                                                                                      int lr, int seg, float (&acc)[P * NGH]) {
         static_assert(G0::b(0) == G0::b(2) && G0::b(1) == G0::b(3) && G1::b(0) == G1::b(2) && G1::b(1) == G1::b(3), "phase pairing");
         F2 pe[NGH], po[NGH];
@@ -859,7 +859,7 @@ struct Inv2d {
         for (int g = 0; g < NGH; ++g) { acc[4 * g] = pe[g].x; acc[4 * g + 1] = po[g].x; acc[4 * g + 2] = pe[g].y; acc[4 * g + 3] = po[g].y; }
     }
     template <class GG = G0>
-    static DTCWT_D typename std::enable_if<!(GG::P == 4 && GG::Q == 2)>::type rows_packed(const Args&, const float*, const float*, int, int,
+    static DTCWT_D typename std::enable_if<!(GG::P == 4 && GG::Q == 2 && (GG::K & 1))>::type rows_packed(const Args&, const float*, const float*, int, int,
                                                                                         float (&)[P * NGH]) {}
 
     // phase 1: row pass out = H:g0(y1) + H:g1(y2); one task = one output row x 4 input columns
@@ -875,26 +875,27 @@ struct Inv2d {
 #pragma unroll
             for (int i = 0; i < P * NGH; ++i) acc[i] = 0.f;
             float w[WN];
-            if (P == 4 && Q == 2 && a.packed_rows) {
+            if (P == 4 && Q == 2 && (G0::K & 1) && a.packed_rows) {
                 rows_packed(a, y1, y2, lr, seg, acc);
             } else {
-                const F4* src = reinterpret_cast<const F4*>(y1 + lr * CY + seg * 4);
+                {
+                    const F4* src = reinterpret_cast<const F4*>(y1 + lr * CY + seg * 4);
 #pragma unroll
-                for (int c = 0; c < WN / 4; ++c) {
-                    const F4 v = src[c];
-                    w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+                    for (int c = 0; c < WN / 4; ++c) {
+                        const F4 v = src[c];
+                        w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+                    }
+                    fir_gather<G0, NGH, HLC, WN>(w, a.g0, acc);
                 }
-                fir_gather<G0, NGH, HLC, WN>(w, a.g0, acc);
-            }
-            {
-                const F4* src = reinterpret_cast<const F4*>(y2 + lr * CY + seg * 4);
+                {
+                    const F4* src = reinterpret_cast<const F4*>(y2 + lr * CY + seg * 4);
 #pragma unroll
-                for (int c = 0; c < WN / 4; ++c) {
-                    const F4 v = src[c];
-                    w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+                    for (int c = 0; c < WN / 4; ++c) {
+                        const F4 v = src[c];
+                        w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+                    }
+                    fir_gather<G1, NGH, HLC, WN>(w, a.g1, acc);
                 }
-                fir_gather<G1, NGH, HLC, WN>(w, a.g1, acc);
-            }
             }
             const int c0 = (P / Q) * (TWI * bx + 4 * seg) - a.crop_c;     // first output column of the task
             float* d = img + (int64_t)r * a.out_cols + c0;

@@ -58,6 +58,21 @@ struct Z3Fwd {
     // gid -> (x pair, y pair, depth group, image s, volume)
     static DTCWT_HD int64_t total(const Args& a) { return (int64_t)(a.w / 2) * (a.h / 2) * groups(a) * 4 * a.n; }
 
+    template <bool INSIDE>
+    static DTCWT_D void accumulate(const Args& a, const float* src, int64_t plane, int l0, int z0, F2 (&lo)[2][NOUT], F2 (&hi)[2][NOUT]) {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            const int z = INSIDE ? z0 + j : unpad(reflect_any(l0 + j, a.L0), a.pad0, a.d0);
+            const float* p = src + (int64_t)z * plane;
+            const F2 v0 = *reinterpret_cast<const F2*>(p);
+            const F2 v1 = *reinterpret_cast<const F2*>(p + a.w);
+            fir_scatter<FLO, NG, HL>(j, v0, a.lo, lo[0]);
+            fir_scatter<FLO, NG, HL>(j, v1, a.lo, lo[1]);
+            fir_scatter<FHI, NG, HL>(j, v0, a.hi, hi[0]);
+            fir_scatter<FHI, NG, HL>(j, v1, a.hi, hi[1]);
+        }
+    }
+
     static DTCWT_D void run(const Args& a, int64_t gid) {
         const int wp = a.w / 2, hp = a.h / 2;
         const int xp = (int)(gid % wp);
@@ -76,18 +91,10 @@ struct Z3Fwd {
         for (int i = 0; i < NOUT; ++i) { lo[0][i] = zero2(); lo[1][i] = zero2(); hi[0][i] = zero2(); hi[1][i] = zero2(); }
         const int l0 = Q * NG * gz - HL;
         const int z0 = l0 - a.pad0;
-        const bool inside = z0 >= 0 && z0 + NR <= a.d0;          // no symmetric extension needed: skip reflect_any's modulo
-#pragma unroll
-        for (int j = 0; j < NR; ++j) {
-            const int z = inside ? z0 + j : unpad(reflect_any(l0 + j, a.L0), a.pad0, a.d0);
-            const float* p = src + (int64_t)z * plane;
-            const F2 v0 = *reinterpret_cast<const F2*>(p);
-            const F2 v1 = *reinterpret_cast<const F2*>(p + a.w);
-            fir_scatter<FLO, NG, HL>(j, v0, a.lo, lo[0]);
-            fir_scatter<FLO, NG, HL>(j, v1, a.lo, lo[1]);
-            fir_scatter<FHI, NG, HL>(j, v0, a.hi, hi[0]);
-            fir_scatter<FHI, NG, HL>(j, v1, a.hi, hi[1]);
-        }
+        // no symmetric extension needed when the window lies inside the stored slices: skip reflect_any's modulo (two copies
+        // of the unrolled loop behind one warp-uniform branch)
+        if (z0 >= 0 && z0 + NR <= a.d0) accumulate<true>(a, src, plane, l0, z0, lo, hi);
+        else accumulate<false>(a, src, plane, l0, z0, lo, hi);
         const int t1 = sub & 1, t2 = sub >> 1;                   // filter types of this image along axes 1 and 2
         const int Lout = a.L0 * P / Q;
         const int zo = NOUT * gz;                                 // first output slice

@@ -264,6 +264,23 @@ int dtcwt_b200_sample_f64(const double *im, double *out, const double *xs, const
                           int64_t i_c, int64_t o_n, int64_t o_y, int64_t o_x, int64_t o_c, int64_t coord_n,
                           int is_complex, int method, int coords, const double *wx, const double *wy, void *stream);
 
+/* ---- keypoints (float64 arithmetic) ---------------------------------------------------
+ * replaces the per-pixel work of dtcwt/keypoint.py (find_keypoints :9-141):
+ *   kp_energy  the keypoint-energy map of one level's six sub-bands (:143-156): method 0 fauqueur (scale_gain =
+ *              alpha**(scale+1), beta), 1 bendale, 2 kingsbury (kappa); yh element (b, band, i, j) at
+ *              2*(b*s_n + band*s_band + i*s_row + j*s_col); e is [n][h][w] float64
+ *   kp_maxima  _kp_energy_maxima (:201-260): out [n][h][w][4] = (1 if the pixel is a kept local maximum else 0,
+ *              refined row, refined column, energy); refine != 0 fits the quadratic patch (:221-252)
+ */
+int dtcwt_b200_kp_energy_f32(const float *yh, double *e, int64_t n, int64_t h, int64_t w, int64_t s_n, int64_t s_band,
+                             int64_t s_row, int64_t s_col, int method, double scale_gain, double beta, double kappa,
+                             void *stream);
+int dtcwt_b200_kp_energy_f64(const double *yh, double *e, int64_t n, int64_t h, int64_t w, int64_t s_n, int64_t s_band,
+                             int64_t s_row, int64_t s_col, int method, double scale_gain, double beta, double kappa,
+                             void *stream);
+int dtcwt_b200_kp_maxima(const double *x, double *out, int64_t n, int64_t h, int64_t w, double threshold, int refine,
+                         void *stream);
+
 #ifdef __cplusplus
 }
 #endif

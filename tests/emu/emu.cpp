@@ -20,6 +20,7 @@
 #include "../../dtcwt_b200/csrc/stream2d.cuh"
 #include "../../dtcwt_b200/csrc/fused3d.cuh"
 #include "../../dtcwt_b200/csrc/registration.cuh"
+#include "../../dtcwt_b200/csrc/keypoint.cuh"
 #include "../../dtcwt_b200/csrc/axis_pass.cuh"
 
 namespace dtcwt {
