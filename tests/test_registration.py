@@ -131,3 +131,28 @@ def test_estimatereg_vs_live_reference_1080p(backend):
     # float32 pyramids: the reference's confidence / phase arithmetic is complex64; median and worst-case agreement
     err = np.abs(got - want)
     assert np.median(err) < 1e-5 and err.max() < 1e-3, (np.median(err), err.max())
+
+
+@pytest.mark.parametrize("method,kw", [("fauqueur", {}), ("bendale", {"refine_positions": False}), ("kingsbury", {"threshold": 0.01, "max_points": 40}),
+                                        ("fauqueur", {"upsample_keypoint_energy": "bilinear", "upsample_highpasses": "lanczos", "skip_levels": 2})])
+def test_find_keypoints_vs_live_reference(backend, method, kw):
+    """dtcwt.keypoint.find_keypoints (reference keypoint.py:9-141) on the same sub-bands: same points, positions, scales and
+    energies.  The reference calls numpy.product, removed in NumPy 2: aliased to numpy.prod for the comparison."""
+    import refshim
+    if not refshim.available():
+        pytest.skip("reference not installed (oracle/_ref)")
+    refshim.load()
+    if not hasattr(np, "product"):
+        np.product = np.prod
+    import dtcwt.keypoint as K
+    f1 = reg_frames((160, 224), seed=11)[0]
+    p = dtcwt_b200.Transform2d().forward(f1, nlevels=4)
+    hp_np = tuple(np.asarray(h) for h in p.highpasses)
+    want = K.find_keypoints(hp_np, method=method, **kw)
+    got = npy(dtcwt_b200.keypoint.find_keypoints(p.highpasses_t, method=method, **kw))
+    assert got.shape == want.shape and got.shape[0] > 5
+    # same multiset of points: sort both by (scale, y, x) before comparing (ties in energy may be ordered differently)
+    def canon(k):
+        return k[np.lexsort((np.round(k[:, 0], 6), np.round(k[:, 1], 6), k[:, 2]))]
+    assert np.abs(canon(got) - canon(want)).max() < 1e-6 * max(1.0, np.abs(want).max())
+    assert np.all(np.diff(got[:, 3]) <= 1e-12)              # sorted by decreasing energy
