@@ -109,6 +109,30 @@ def _taps(h):
     return out
 
 
+_SCRATCH = {}       # (tag, shape, dtype, device, stream) -> tensor
+
+
+def scratch(tag, shape, dtype, device):
+    """Reusable device scratch for buffers that never leave a transform call (the four per-slice images of a 3-D
+    level, LoLo intermediates of a 2-D forward without include_scale): one buffer per (purpose, shape, stream), so a
+    steady-state loop of transforms allocates nothing.  Work on one stream is ordered, so reusing the buffer in the next
+    call on that stream is safe; another stream gets its own."""
+    stream = torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0
+    key = (tag, tuple(int(s) for s in shape), dtype, str(device), stream)
+    t = _SCRATCH.get(key)
+    if t is None:
+        if len(_SCRATCH) > 64:
+            _SCRATCH.clear()
+        t = torch.empty(key[1], dtype=dtype, device=device)
+        _SCRATCH[key] = t
+    return t
+
+
+def release_scratch():
+    """Drop the cached scratch buffers (they are otherwise kept for the life of the process)."""
+    _SCRATCH.clear()
+
+
 def _view(shape, axis):
     outer = int(np.prod(shape[:axis], dtype=np.int64))
     inner = int(np.prod(shape[axis + 1:], dtype=np.int64))
@@ -205,16 +229,17 @@ def _fused_ok(*tensors):
     return FUSED_ENABLED and all(t.dtype in (torch.float32, torch.complex64) for t in tensors)
 
 
-def fwd2d_level1(x, h0o, h1o, pad_hi):
+def fwd2d_level1(x, h0o, h1o, pad_hi, internal=False):
     """Fused level 1 of the 2-D forward transform: x [n][H][W] -> (LoLo [n][H'][W'], Yh planar [n][6][H'/2][W'/2])
-    or None when the fused kernels do not cover the request."""
+    or None when the fused kernels do not cover the request.  internal: LoLo is only the next level's input (not
+    returned to the user) and lives in reusable scratch."""
     if not _fused_ok(x):
         return None
     n, r, c = x.shape
     Lr, Lc = r + pad_hi[0], c + pad_hi[1]
     k0, p0, m0 = _taps(h0o)
     k1, p1, m1 = _taps(h1o)
-    lolo = torch.empty((n, Lr, Lc), dtype=x.dtype, device=x.device)
+    lolo = scratch("lolo1", (n, Lr, Lc), x.dtype, x.device) if internal else torch.empty((n, Lr, Lc), dtype=x.dtype, device=x.device)
     yh = new_highpass(n, 6, (Lr // 2, Lc // 2), x.dtype, x.device)
     with _on_device(x):
         ok = _lib.call_optional("fwd2d_level1", "f32", _ptr(x), _ptr(lolo), _ptr(yh), n, r, c, pad_hi[0], pad_hi[1],
@@ -222,8 +247,9 @@ def fwd2d_level1(x, h0o, h1o, pad_hi):
     return (lolo, yh) if ok else None
 
 
-def fwd2d_levelq(x, lo_a, lo_b, hi_a, hi_b, pad):
-    """Fused level >= 2 of the 2-D forward transform; pad = (pad_r, pad_c) in {0, 1} (one sample each side)."""
+def fwd2d_levelq(x, lo_a, lo_b, hi_a, hi_b, pad, internal=None):
+    """Fused level >= 2 of the 2-D forward transform; pad = (pad_r, pad_c) in {0, 1} (one sample each side).
+    internal: a tag when LoLo is only the next level's input (reusable scratch)."""
     if not _fused_ok(x):
         return None
     n, r, c = x.shape
@@ -231,7 +257,10 @@ def fwd2d_levelq(x, lo_a, lo_b, hi_a, hi_b, pad):
     taps = [_taps(h) for h in (lo_a, lo_b, hi_a, hi_b)]
     if len({t[2] for t in taps}) != 1:
         return None
-    lolo = torch.empty((n, Lr // 2, Lc // 2), dtype=x.dtype, device=x.device)
+    if internal:
+        lolo = scratch(internal, (n, Lr // 2, Lc // 2), x.dtype, x.device)
+    else:
+        lolo = torch.empty((n, Lr // 2, Lc // 2), dtype=x.dtype, device=x.device)
     yh = new_highpass(n, 6, (Lr // 4, Lc // 4), x.dtype, x.device)
     with _on_device(x):
         ok = _lib.call_optional("fwd2d_levelq", "f32", _ptr(x), _ptr(lolo), _ptr(yh), n, r, c, pad[0], pad[1],
@@ -327,9 +356,9 @@ def lowpass3d(x, h, inverse=False):
     n, d0, d1, d2 = x.shape
     k, p, m = _taps(h)
     y = torch.empty_like(x)
-    scratch = torch.empty_like(x)
+    scr = scratch("low3d", x.shape, x.dtype, x.device)
     with _on_device(x):
-        ok = _lib.call_optional("inv3d_level1_lo" if inverse else "fwd3d_level1_lo", "f32", _ptr(x), _ptr(y), _ptr(scratch),
+        ok = _lib.call_optional("inv3d_level1_lo" if inverse else "fwd3d_level1_lo", "f32", _ptr(x), _ptr(y), _ptr(scr),
                                 n, d0, d1, d2, p, m, _stream(x))
     return y if ok else None
 
@@ -345,9 +374,9 @@ def fwd3d_level1(x, h0o, h1o):
     k1, p1, m1 = _taps(h1o)
     lll = torch.empty_like(x)
     yh = new_highpass(n, 28, (d0 // 2, d1 // 2, d2 // 2), x.dtype, x.device)
-    scratch = torch.empty((4,) + tuple(x.shape), dtype=x.dtype, device=x.device)
+    scr = scratch("fwd3d1", (4,) + tuple(x.shape), x.dtype, x.device)
     with _on_device(x):
-        ok = _lib.call_optional("fwd3d_level1", "f32", _ptr(x), _ptr(lll), _ptr(yh), _ptr(scratch), n, d0, d1, d2,
+        ok = _lib.call_optional("fwd3d_level1", "f32", _ptr(x), _ptr(lll), _ptr(yh), _ptr(scr), n, d0, d1, d2,
                                 p0, m0, p1, m1, *_chan_strides(yh), _stream(x))
     return (lll, yh) if ok else None
 
@@ -366,9 +395,9 @@ def fwd3d_levelq(x, lo_a, lo_b, hi_a, hi_b, pads):
         return None
     lll = torch.empty((n, L[0] // 2, L[1] // 2, L[2] // 2), dtype=x.dtype, device=x.device)
     yh = new_highpass(n, 28, (L[0] // 4, L[1] // 4, L[2] // 4), x.dtype, x.device)
-    scratch = torch.empty((n * d0 * L[1] * L[2],), dtype=x.dtype, device=x.device)
+    scr = scratch("fwd3dq", (n * d0 * L[1] * L[2],), x.dtype, x.device)
     with _on_device(x):
-        ok = _lib.call_optional("fwd3d_levelq", "f32", _ptr(x), _ptr(lll), _ptr(yh), _ptr(scratch), n, d0, d1, d2,
+        ok = _lib.call_optional("fwd3d_levelq", "f32", _ptr(x), _ptr(lll), _ptr(yh), _ptr(scr), n, d0, d1, d2,
                                 pads[0], pads[1], pads[2], taps[0][1], taps[1][1], taps[2][1], taps[3][1], taps[0][2],
                                 *_chan_strides(yh), _stream(x))
     return (lll, yh) if ok else None
@@ -384,9 +413,9 @@ def inv3d_levelq(yl, yh, lo_a, lo_b, hi_a, hi_b, crops):
         return None
     od = (2 * a0 - 2 * crops[0], 2 * a1 - 2 * crops[1], 2 * a2 - 2 * crops[2])
     out = torch.empty((n,) + od, dtype=yl.dtype, device=yl.device)
-    scratch = torch.empty((4 * n * od[0] * a1 * a2,), dtype=yl.dtype, device=yl.device)
+    scr = scratch("inv3dq", (4 * n * od[0] * a1 * a2,), yl.dtype, yl.device)
     with _on_device(yl):
-        ok = _lib.call_optional("inv3d_levelq", "f32", _ptr(yl), _ptr(yh), _ptr(out), _ptr(scratch), n, a0, a1, a2,
+        ok = _lib.call_optional("inv3d_levelq", "f32", _ptr(yl), _ptr(yh), _ptr(out), _ptr(scr), n, a0, a1, a2,
                                 crops[0], crops[1], crops[2], taps[0][1], taps[1][1], taps[2][1], taps[3][1], taps[0][2],
                                 *_chan_strides(yh), _stream(yl))
     return out if ok else None
@@ -400,8 +429,8 @@ def inv3d_level1(yl, yh, g0o, g1o):
     k0, p0, m0 = _taps(g0o)
     k1, p1, m1 = _taps(g1o)
     out = torch.empty_like(yl)
-    scratch = torch.empty((4,) + tuple(yl.shape), dtype=yl.dtype, device=yl.device)
+    scr = scratch("inv3d1", (4,) + tuple(yl.shape), yl.dtype, yl.device)
     with _on_device(yl):
-        ok = _lib.call_optional("inv3d_level1", "f32", _ptr(yl), _ptr(yh), _ptr(out), _ptr(scratch), n, a0, a1, a2,
+        ok = _lib.call_optional("inv3d_level1", "f32", _ptr(yl), _ptr(yh), _ptr(out), _ptr(scr), n, a0, a1, a2,
                                 p0, m0, p1, m1, *_chan_strides(yh), _stream(yl))
     return out if ok else None

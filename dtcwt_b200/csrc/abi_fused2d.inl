@@ -158,19 +158,7 @@ static int inv_common(Inv2dArgs& a, const float* z, const float* yh, float* out,
     a.out_vec4 = (crop_c == 0 && (a.out_cols % 4) == 0 && aligned_to(out, 16)) ? 1 : 0;
     a.zs_n = zs_n; a.zs_band = zs_band; a.zs_row = zs_row;
     for (int b = 0; b < 6; ++b) a.gain[b] = (float)(gain[b] * kInvSqrt2);
-    a.packed_rows = 0;
     return DTCWT_B200_OK;
-}
-
-// tap pairs of the packed q-shift row pass (Inv2d::rows_packed, InvSq::rows): phases (0, 2) and (1, 3) of each filter
-static void int_pair_tabs(PairTab (&q)[4], const PhaseTaps& g0, const PhaseTaps& g1, int m) {
-    for (int k = 0; k <= kStreamMaxTaps; ++k) {
-        const bool in = k < m / 2;
-        q[0].p[k].x = in ? g0.t[0][k] : 0.f; q[0].p[k].y = in ? g0.t[2][k] : 0.f;
-        q[1].p[k].x = in ? g1.t[0][k] : 0.f; q[1].p[k].y = in ? g1.t[2][k] : 0.f;
-        q[2].p[k].x = in ? g0.t[1][k] : 0.f; q[2].p[k].y = in ? g0.t[3][k] : 0.f;
-        q[3].p[k].x = in ? g1.t[1][k] : 0.f; q[3].p[k].y = in ? g1.t[3][k] : 0.f;
-    }
 }
 
 }  // namespace dtcwt
@@ -296,8 +284,6 @@ int dtcwt_b200_inv2d_levelq_f32(const float* z, const float* yh, float* out, int
     if (rc) return rc;
     taps_int(a.g0, lo_a, lo_b, m, true);
     taps_int(a.g1, hi_a, hi_b, m, false);
-    int_pair_tabs(a.q, a.g0, a.g1, m);
-    a.packed_rows = (((m / 2) & 1) && env_int("DTCWT_B200_INVQ_PACKED", 0)) ? 1 : 0;      // m/2 odd: phases (ph, ph+2) share their samples
     if (cols >= (1 << 27) || zs_row >= (1 << 27)) return DTCWT_B200_EUNSUPPORTED;   // byte strides are 32-bit
     // The streaming kernel is parity-tested but measured no faster than the tile kernel on level 2 and slower on the small
     // levels (few, long CTAs): profiles/r1_04.  It is selected with DTCWT_B200_INV_STREAM=1.

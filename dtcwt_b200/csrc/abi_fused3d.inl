@@ -249,8 +249,6 @@ int dtcwt_b200_inv3d_levelq_f32(const float* yl, const float* yh, float* out, fl
     for (int b = 0; b < 6; ++b) a.gain[b] = 1.f;
     taps_int(a.g0, lo_a, lo_b, m, true);
     taps_int(a.g1, hi_a, hi_b, m, false);
-    int_pair_tabs(a.q, a.g0, a.g1, m);
-    a.packed_rows = (((m / 2) & 1) && env_int("DTCWT_B200_INVQ_PACKED", 0)) ? 1 : 0;
     if (m == 10) return launch_inv2d<InvLqRaw<10>::type>(a, stream);
     if (m == 14) return launch_inv2d<InvLqRaw<14>::type>(a, stream);
     if (m == 16) return launch_inv2d<InvLqRaw<16>::type>(a, stream);
@@ -285,7 +283,6 @@ int dtcwt_b200_inv3d_level1_f32(const float* yl, const float* yh, float* out, fl
     a.out_vec4 = ((a.out_cols % 4) == 0) ? 1 : 0;
     a.zs_n = 0; a.zs_band = sub; a.zs_row = 0;
     for (int b = 0; b < 6; ++b) a.gain[b] = 1.f;
-    a.packed_rows = 0;
     taps_col(a.g0, g0o, m0, 19, 1.0); taps_col(a.g1, g1o, m1, 19, 1.0);
     return launch_inv2d<InvT1Raw>(a, stream);
 }

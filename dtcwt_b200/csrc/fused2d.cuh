@@ -657,8 +657,6 @@ struct Inv2dArgs {
     int64_t zs_n, zs_band, zs_row;
     float gain[6];                  // gain_mask column of this level, times 1/sqrt2
     PhaseTaps g0, g1;
-    PairTab q[4];                   // q-shift row pass, packed: (g0 phases 0,2) (g1 phases 0,2) (g0 phases 1,3) (g1 phases 1,3)
-    int packed_rows;                // 1: row pass with the tap pairs above (two outputs per FFMA2)
 };
 
 // Column pass first: each thread owns one quad column (two adjacent real columns), NGV groups of rows
@@ -826,42 +824,6 @@ struct Inv2d {
         }
     }
 
-    // q-shift row pass, packed (m/2 odd): output phases ph and ph + 2 of a group read the same samples (SpecInt::b), so one
-    // FFMA2 of a scalar sample with the tap pair (t[ph][k], t[ph+2][k]) advances both -- half the issue slots of the scalar
-    // form below.  pe[g] = outputs (0, 2), po[g] = outputs (1, 3) of group g.
-    template <class GG = G0>
-    static DTCWT_D typename std::enable_if<GG::P == 4 && GG::Q == 2 && (GG::K & 1)>::type rows_packed(const Args& a, const float* y1, const float* y2,
-                                                                                     int lr, int seg, float (&acc)[P * NGH]) {
-        static_assert(G0::b(0) == G0::b(2) && G0::b(1) == G0::b(3) && G1::b(0) == G1::b(2) && G1::b(1) == G1::b(3), "phase pairing");
-        F2 pe[NGH], po[NGH];
-#pragma unroll
-        for (int g = 0; g < NGH; ++g) { pe[g] = zero2(); po[g] = zero2(); }
-        const F4* s1 = reinterpret_cast<const F4*>(y1 + lr * CY + seg * 4);
-        const F4* s2 = reinterpret_cast<const F4*>(y2 + lr * CY + seg * 4);
-#pragma unroll
-        for (int c = 0; c < WN / 4; ++c) {
-            const F4 v1 = s1[c], v2 = s2[c];
-            const float w1[4] = {v1.x, v1.y, v1.z, v1.w}, w2[4] = {v2.x, v2.y, v2.z, v2.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-#pragma unroll
-                for (int g = 0; g < NGH; ++g) {
-                    const int j = 4 * c + i - HLC - Q * g;                 // sample index relative to the group's first input
-                    const int n00 = j - G0::b(0), n01 = j - G0::b(1), n10 = j - G1::b(0), n11 = j - G1::b(1);
-                    if (n00 >= 0 && (n00 % 2) == 0 && n00 / 2 < G0::K) pe[g] = fma2(w1[i], a.q[0].p[n00 / 2], pe[g]);
-                    if (n01 >= 0 && (n01 % 2) == 0 && n01 / 2 < G0::K) po[g] = fma2(w1[i], a.q[2].p[n01 / 2], po[g]);
-                    if (n10 >= 0 && (n10 % 2) == 0 && n10 / 2 < G1::K) pe[g] = fma2(w2[i], a.q[1].p[n10 / 2], pe[g]);
-                    if (n11 >= 0 && (n11 % 2) == 0 && n11 / 2 < G1::K) po[g] = fma2(w2[i], a.q[3].p[n11 / 2], po[g]);
-                }
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < NGH; ++g) { acc[4 * g] = pe[g].x; acc[4 * g + 1] = po[g].x; acc[4 * g + 2] = pe[g].y; acc[4 * g + 3] = po[g].y; }
-    }
-    template <class GG = G0>
-    static DTCWT_D typename std::enable_if<!(GG::P == 4 && GG::Q == 2 && (GG::K & 1))>::type rows_packed(const Args&, const float*, const float*, int, int,
-                                                                                        float (&)[P * NGH]) {}
-
     // phase 1: row pass out = H:g0(y1) + H:g1(y2); one task = one output row x 4 input columns
     static DTCWT_D void phase_rows(const Args& a, float* sm, int bx, int by, int bz, int tid) {
         const float* y1 = sm;
@@ -875,27 +837,23 @@ struct Inv2d {
 #pragma unroll
             for (int i = 0; i < P * NGH; ++i) acc[i] = 0.f;
             float w[WN];
-            if (P == 4 && Q == 2 && (G0::K & 1) && a.packed_rows) {
-                rows_packed(a, y1, y2, lr, seg, acc);
-            } else {
-                {
-                    const F4* src = reinterpret_cast<const F4*>(y1 + lr * CY + seg * 4);
+            {
+                const F4* src = reinterpret_cast<const F4*>(y1 + lr * CY + seg * 4);
 #pragma unroll
-                    for (int c = 0; c < WN / 4; ++c) {
-                        const F4 v = src[c];
-                        w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
-                    }
-                    fir_gather<G0, NGH, HLC, WN>(w, a.g0, acc);
+                for (int c = 0; c < WN / 4; ++c) {
+                    const F4 v = src[c];
+                    w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
                 }
-                {
-                    const F4* src = reinterpret_cast<const F4*>(y2 + lr * CY + seg * 4);
+                fir_gather<G0, NGH, HLC, WN>(w, a.g0, acc);
+            }
+            {
+                const F4* src = reinterpret_cast<const F4*>(y2 + lr * CY + seg * 4);
 #pragma unroll
-                    for (int c = 0; c < WN / 4; ++c) {
-                        const F4 v = src[c];
-                        w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
-                    }
-                    fir_gather<G1, NGH, HLC, WN>(w, a.g1, acc);
+                for (int c = 0; c < WN / 4; ++c) {
+                    const F4 v = src[c];
+                    w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
                 }
+                fir_gather<G1, NGH, HLC, WN>(w, a.g1, acc);
             }
             const int c0 = (P / Q) * (TWI * bx + 4 * seg) - a.crop_c;     // first output column of the task
             float* d = img + (int64_t)r * a.out_cols + c0;

@@ -178,6 +178,50 @@ struct Z3Inv {
         o.v[1][1].y = -p.y + q.y + r.y - s.y;       // H
     }
 
+    template <bool INSIDE>
+    static DTCWT_D void accumulate(const Args& a, F2 (&acc)[2][NOUT], int sub, int b, int yp, int xp, int o0, int noct, int64_t plane,
+                                   int t1, int t2) {
+#pragma unroll
+        for (int jq = 0; jq < NR / 2; ++jq) {
+            // symmetric extension at octet granularity: a mirrored octet has its axis-0 parities exchanged
+            int oz = o0 + jq;
+            bool flip = false;
+            if (!INSIDE) {
+                if (oz < 0) { oz = -1 - oz; flip = true; } else if (oz >= noct) { oz = 2 * noct - 1 - oz; flip = true; }
+                oz = oz < 0 ? 0 : (oz >= noct ? noct - 1 : oz);     // further out only feeds outputs that are never stored
+            }
+            Oct lo, hi;
+            if (sub == 0) {
+                const float* p = a.s + ((int64_t)b * a.d0 + 2 * oz) * plane + (int64_t)(2 * yp) * a.w + 2 * xp;
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+#pragma unroll
+                    for (int f = 0; f < 2; ++f) {
+                        const F2 v = *reinterpret_cast<const F2*>(p + (int64_t)e * plane + (int64_t)f * a.w);
+                        lo.v[e][f].x = 2.f * v.x; lo.v[e][f].y = 2.f * v.y;
+                    }
+            } else {
+                unpack(a, octant_block(0, t1, t2), b, oz, yp, xp, lo);
+            }
+            unpack(a, octant_block(1, t1, t2), b, oz, yp, xp, hi);
+            if (!INSIDE && flip) {                                          // selects, not indexed: the octets stay in registers
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+                    F2 t = lo.v[0][f]; lo.v[0][f] = lo.v[1][f]; lo.v[1][f] = t;
+                    t = hi.v[0][f]; hi.v[0][f] = hi.v[1][f]; hi.v[1][f] = t;
+                }
+            }
+            fir_scatter<GLO, NG, HL>(2 * jq, lo.v[0][0], a.lo, acc[0]);
+            fir_scatter<GLO, NG, HL>(2 * jq, lo.v[0][1], a.lo, acc[1]);
+            fir_scatter<GHI, NG, HL>(2 * jq, hi.v[0][0], a.hi, acc[0]);
+            fir_scatter<GHI, NG, HL>(2 * jq, hi.v[0][1], a.hi, acc[1]);
+            fir_scatter<GLO, NG, HL>(2 * jq + 1, lo.v[1][0], a.lo, acc[0]);
+            fir_scatter<GLO, NG, HL>(2 * jq + 1, lo.v[1][1], a.lo, acc[1]);
+            fir_scatter<GHI, NG, HL>(2 * jq + 1, hi.v[1][0], a.hi, acc[0]);
+            fir_scatter<GHI, NG, HL>(2 * jq + 1, hi.v[1][1], a.hi, acc[1]);
+        }
+    }
+
     static DTCWT_D void run(const Args& a, int64_t gid) {
         const int wp = a.w / 2, hp = a.h / 2;
         const int xp = (int)(gid % wp);
@@ -196,43 +240,9 @@ struct Z3Inv {
 #pragma unroll
         for (int i = 0; i < NOUT; ++i) { acc[0][i] = zero2(); acc[1][i] = zero2(); }
         const int o0 = (Q * NG * gz - HL) / 2;                   // first octet along axis 0 (may be negative)
-#pragma unroll
-        for (int jq = 0; jq < NR / 2; ++jq) {
-            // symmetric extension at octet granularity: a mirrored octet has its axis-0 parities exchanged
-            int oz = o0 + jq;
-            bool flip = false;
-            if (oz < 0) { oz = -1 - oz; flip = true; } else if (oz >= noct) { oz = 2 * noct - 1 - oz; flip = true; }
-            oz = oz < 0 ? 0 : (oz >= noct ? noct - 1 : oz);     // further out only feeds outputs that are never stored
-            Oct lo, hi;
-            if (sub == 0) {
-                const float* p = a.s + ((int64_t)b * a.d0 + 2 * oz) * plane + (int64_t)(2 * yp) * a.w + 2 * xp;
-#pragma unroll
-                for (int e = 0; e < 2; ++e)
-#pragma unroll
-                    for (int f = 0; f < 2; ++f) {
-                        const F2 v = *reinterpret_cast<const F2*>(p + (int64_t)e * plane + (int64_t)f * a.w);
-                        lo.v[e][f].x = 2.f * v.x; lo.v[e][f].y = 2.f * v.y;
-                    }
-            } else {
-                unpack(a, octant_block(0, t1, t2), b, oz, yp, xp, lo);
-            }
-            unpack(a, octant_block(1, t1, t2), b, oz, yp, xp, hi);
-            if (flip) {                                          // selects, not indexed: the octets stay in registers
-#pragma unroll
-                for (int f = 0; f < 2; ++f) {
-                    F2 t = lo.v[0][f]; lo.v[0][f] = lo.v[1][f]; lo.v[1][f] = t;
-                    t = hi.v[0][f]; hi.v[0][f] = hi.v[1][f]; hi.v[1][f] = t;
-                }
-            }
-            fir_scatter<GLO, NG, HL>(2 * jq, lo.v[0][0], a.lo, acc[0]);
-            fir_scatter<GLO, NG, HL>(2 * jq, lo.v[0][1], a.lo, acc[1]);
-            fir_scatter<GHI, NG, HL>(2 * jq, hi.v[0][0], a.hi, acc[0]);
-            fir_scatter<GHI, NG, HL>(2 * jq, hi.v[0][1], a.hi, acc[1]);
-            fir_scatter<GLO, NG, HL>(2 * jq + 1, lo.v[1][0], a.lo, acc[0]);
-            fir_scatter<GLO, NG, HL>(2 * jq + 1, lo.v[1][1], a.lo, acc[1]);
-            fir_scatter<GHI, NG, HL>(2 * jq + 1, hi.v[1][0], a.hi, acc[0]);
-            fir_scatter<GHI, NG, HL>(2 * jq + 1, hi.v[1][1], a.hi, acc[1]);
-        }
+        // windows inside the volume skip the mirror logic (two copies of the unrolled loop, one warp-uniform branch)
+        if (o0 >= 0 && o0 + NR / 2 <= noct) accumulate<true>(a, acc, sub, b, yp, xp, o0, noct, plane, t1, t2);
+        else accumulate<false>(a, acc, sub, b, yp, xp, o0, noct, plane, t1, t2);
         float* d = a.lll + sub * a.sub_stride + b * a.vol_stride + (int64_t)(2 * yp) * a.w + 2 * xp;
 #pragma unroll
         for (int i = 0; i < NOUT; ++i) {

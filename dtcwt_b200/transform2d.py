@@ -233,11 +233,12 @@ class Transform2d(object):
         if t["h0o"].shape[0] % 2 == 0 or t["h1o"].shape[0] % 2 == 0:
             raise ValueError("even-length biorthogonal filters are not supported by the 2-D transform")
         Yh, Ysc = [], []
-        LoLo, yh = self._fwd_level1(X, t, ph, pw)
+        # a LoLo that is only the next level's input (not the pyramid's lowpass, not a requested scale) is scratch
+        LoLo, yh = self._fwd_level1(X, t, ph, pw, internal=(nlevels > 1 and not include_scale))
         Yh.append(yh)
         Ysc.append(LoLo)
-        for _ in range(1, nlevels):
-            LoLo, yh = self._fwd_levelq(LoLo, t)
+        for lev in range(1, nlevels):
+            LoLo, yh = self._fwd_levelq(LoLo, t, internal=("lolo%d" % (lev + 1)) if (lev < nlevels - 1 and not include_scale) else None)
             Yh.append(yh)
             Ysc.append(LoLo)
         if ph or pw:
@@ -248,11 +249,11 @@ class Transform2d(object):
         views = tuple(h.permute(0, 2, 3, 1) for h in Yh)         # [N][h][w][6] views of planar storage
         return Pyramid(LoLo, views, tuple(Ysc)) if include_scale else Pyramid(LoLo, views)
 
-    def _fwd_level1(self, X, t, ph, pw):
+    def _fwd_level1(self, X, t, ph, pw, internal=False):
         """Level 1 (reference :112-130): undecimated biort filters, vertical axis first."""
         N = X.shape[0]
         if t["h2o"] is None:
-            fused = _ops.fwd2d_level1(X, t["h0o"], t["h1o"], (ph, pw))
+            fused = _ops.fwd2d_level1(X, t["h0o"], t["h1o"], (ph, pw), internal)
             if fused is not None:
                 return fused
         Lo = _ops.colfilter(X, t["h0o"], 1, (0, ph))
@@ -268,13 +269,13 @@ class Transform2d(object):
             _ops.q2c(_ops.colfilter(Hi, t["h1o"], 2, (0, pw)), yh, *_BANDS_HH)
         return LoLo, yh
 
-    def _fwd_levelq(self, LoLo, t):
+    def _fwd_levelq(self, LoLo, t, internal=None):
         """Level >= 2 (reference :132-160): decimating q-shift pairs."""
         N, r, c = LoLo.shape
         pr = (1, 1) if r % 4 else (0, 0)
         pc = (1, 1) if c % 4 else (0, 0)
         if t["h2a"] is None:
-            fused = _ops.fwd2d_levelq(LoLo, t["h0b"], t["h0a"], t["h1b"], t["h1a"], (pr[0], pc[0]))
+            fused = _ops.fwd2d_levelq(LoLo, t["h0b"], t["h0a"], t["h1b"], t["h1a"], (pr[0], pc[0]), internal)
             if fused is not None:
                 return fused
         Lo = _ops.coldfilt(LoLo, t["h0b"], t["h0a"], 1, pr)
