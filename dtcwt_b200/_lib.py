@@ -46,6 +46,10 @@ _F32_ONLY = {
     "fwd2d_levelq": [_P, _P, _P, _L, _L, _L, _I, _I, _TAPS, _TAPS, _TAPS, _TAPS, _I, _L, _L, _L, _P],
     "inv2d_levelq": [_P, _P, _P, _L, _L, _L, _I, _I, _TAPS, _TAPS, _TAPS, _TAPS, _I, _TAPS, _L, _L, _L, _P],
     "inv2d_level1": [_P, _P, _P, _L, _L, _L, _TAPS, _I, _TAPS, _I, _TAPS, _L, _L, _L, _P],
+    "fwd2d_level1_hh": [_P, _P, _L, _L, _L, _I, _I, _TAPS, _I, _L, _L, _L, _P],
+    "fwd2d_levelq_hh": [_P, _P, _L, _L, _L, _I, _I, _TAPS, _TAPS, _I, _L, _L, _L, _P],
+    "inv2d_levelq_hh": [_P, _P, _L, _L, _L, _I, _I, _TAPS, _TAPS, _I, _TAPS, _L, _L, _L, _P],
+    "inv2d_level1_hh": [_P, _P, _L, _L, _L, _TAPS, _I, _TAPS, _L, _L, _L, _P],
     "fwd3d_level1_lo": [_P, _P, _P, _L, _L, _L, _L, _TAPS, _I, _P],
     "inv3d_level1_lo": [_P, _P, _P, _L, _L, _L, _L, _TAPS, _I, _P],
     "fwd3d_level1": [_P, _P, _P, _P, _L, _L, _L, _L, _TAPS, _I, _TAPS, _I, _L, _L, _L, _L, _L, _P],

@@ -305,6 +305,53 @@ def inv2d_level1(z, yh, g0o, g1o, gain):
     return out if ok else None
 
 
+# `_bp` families: the second launch of a level (bands 1 and 4 from the band-pass pair h2 / g2)
+def fwd2d_level1_hh(x, yh, h2o, pad_hi):
+    if not _fused_ok(x):
+        return False
+    n, r, c = x.shape
+    k, p, m = _taps(h2o)
+    with _on_device(x):
+        return _lib.call_optional("fwd2d_level1_hh", "f32", _ptr(x), _ptr(yh), n, r, c, pad_hi[0], pad_hi[1], p, m,
+                                  yh.stride(0), yh.stride(1), yh.stride(2), _stream(x))
+
+
+def fwd2d_levelq_hh(x, yh, h2_a, h2_b, pad):
+    if not _fused_ok(x):
+        return False
+    n, r, c = x.shape
+    ta, tb = _taps(h2_a), _taps(h2_b)
+    if ta[2] != tb[2]:
+        return False
+    with _on_device(x):
+        return _lib.call_optional("fwd2d_levelq_hh", "f32", _ptr(x), _ptr(yh), n, r, c, pad[0], pad[1], ta[1], tb[1], ta[2],
+                                  yh.stride(0), yh.stride(1), yh.stride(2), _stream(x))
+
+
+def inv2d_levelq_hh(yh, out, rows, cols, g2_a, g2_b, gain, crop):
+    """out += H:g2(V:g2(c2q(bands 1, 4))) for a level >= 2; rows x cols is the level's lowpass size."""
+    if not _fused_ok(yh, out) or not yh.is_contiguous():
+        return False
+    ta, tb = _taps(g2_a), _taps(g2_b)
+    if ta[2] != tb[2]:
+        return False
+    gk, gp = _gain6(gain)
+    with _on_device(out):
+        return _lib.call_optional("inv2d_levelq_hh", "f32", _ptr(yh), _ptr(out), yh.shape[0], rows, cols, crop[0], crop[1],
+                                  ta[1], tb[1], ta[2], gp, yh.stride(0), yh.stride(1), yh.stride(2), _stream(out))
+
+
+def inv2d_level1_hh(yh, out, g2o, gain):
+    if not _fused_ok(yh, out) or not yh.is_contiguous():
+        return False
+    n, r, c = out.shape
+    k, p, m = _taps(g2o)
+    gk, gp = _gain6(gain)
+    with _on_device(out):
+        return _lib.call_optional("inv2d_level1_hh", "f32", _ptr(yh), _ptr(out), n, r, c, p, m, gp,
+                                  yh.stride(0), yh.stride(1), yh.stride(2), _stream(out))
+
+
 # ----------------------------------------------------------------------------- 1-D packing
 def pack1d(hi):
     """real [2k][c] -> complex [k][c]: even rows real part, odd rows imaginary part."""

@@ -113,6 +113,11 @@ typedef InvS1T<19, 13, kMask19, kMask13, 24, 4, BakedTaps<NearSymB_g0>, BakedTap
 typedef InvS1T<19, 19, 0x7ffffu, 0x7ffffu, 24, 6> InvT1_19_19;
 typedef InvS1T<7, 5, 0x7fu, 0x1fu, 8, 4> InvT1_7_5;
 typedef InvS1<7, 5, 0x7fu, 0x1fu, 8, 2> InvL1_7_5;                  // near_sym_a (+ legall 3/5)
+// `_bp` families: the second launch of a level, bands 1 and 4 from the band-pass pair (h2 / g2) in the H1 / G1 slot
+typedef Fwd2d<SpecCol<19>, SpecCol<19>, 64, 64, 8, RtPhase, RtPhase, RtPhase, kFwdHH> FwdT1_hh;
+typedef InvS1<19, 19, 0x7ffffu, 0x7ffffu, 24, 3, ArgTaps, ArgTaps, 2, 0, true> InvL1_hh;
+template <int M> struct FwdLqHH { typedef Fwd2d<SpecDec<M, true>, SpecDec<M, false>, 32, 16, 4, RtPhase, RtPhase, RtPhase, kFwdHH> type; };
+template <int M> struct InvLqHH { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4, false, true> type; };
 // levels >= 2: q-shift pairs; every shipped family has a positive lowpass and a negative highpass tap correlation
 template <int M> struct FwdLq { typedef Fwd2d<SpecDec<M, true>, SpecDec<M, false>, 32, 16, 4> type; };
 template <int M> struct InvLq { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4> type; };
@@ -267,6 +272,51 @@ int dtcwt_b200_fwd2d_levelq_f32(const float* x, float* lolo, float* yh, int64_t 
     if (m == 16) return launch_fwd2d<FwdLq<16>::type>(a, stream);
     return launch_fwd2d<FwdLq<18>::type>(a, stream);
 }
+// transform2d.py:116-121 (`_bp` 6-tuple biort): bands 1 and 4 of level 1 are q2c(V:h2o(H:h2o(X))).  Call AFTER
+// dtcwt_b200_fwd2d_level1_f32 on the same yh: the two diagonal sub-bands are overwritten.
+int dtcwt_b200_fwd2d_level1_hh_f32(const float* x, float* yh, int64_t n, int64_t rows, int64_t cols, int pad_r_hi, int pad_c_hi,
+                                   const double* h2o, int m2, int64_t zs_n, int64_t zs_band, int64_t zs_row, void* stream) {
+    if (!h2o || m2 < 1 || pad_r_hi < 0 || pad_r_hi > 1 || pad_c_hi < 0 || pad_c_hi > 1) return DTCWT_B200_EINVAL;
+    if (!(m2 & 1) || m2 > 19) return DTCWT_B200_EUNSUPPORTED;
+    Fwd2dArgs c;
+    const int rc = fwd_common(c, x, yh, yh, n, rows, cols, 0, pad_r_hi, 0, pad_c_hi, 1, 1, zs_n, zs_band, zs_row);
+    if (rc) return rc;
+    taps_col(c.h0, h2o, m2, 19, 1.0);
+    taps_col(c.h1s, h2o, m2, 19, kInvSqrt2);
+    c.v0 = c.h0;
+    taps_col(c.v1, h2o, m2, 19, 1.0);
+    c.v1s = c.h1s;
+    ColTaps t;
+    taps_col_s(t, h2o, m2, 19, kInvSqrt2);
+    pair_tab(c.ph1s, t, 19);
+    c.ph0 = c.ph1s;
+    return launch_fwd2d<FwdT1_hh>(c, stream);
+}
+
+// transform2d.py:145-157 (`_bp` 12-tuple qshift): bands 1 and 4 of a level >= 2 from the band-pass pair; (h2_a, h2_b) are
+// coldfilt's (ha, hb), i.e. the reference passes (h2b, h2a).  Call AFTER dtcwt_b200_fwd2d_levelq_f32 on the same yh.
+int dtcwt_b200_fwd2d_levelq_hh_f32(const float* x, float* yh, int64_t n, int64_t rows, int64_t cols, int pad_r, int pad_c,
+                                   const double* h2_a, const double* h2_b, int m, int64_t zs_n, int64_t zs_band, int64_t zs_row,
+                                   void* stream) {
+    if (!h2_a || !h2_b || m < 2 || (m & 1) || pad_r < 0 || pad_r > 1 || pad_c < 0 || pad_c > 1) return DTCWT_B200_EINVAL;
+    if (m != 10 && m != 14 && m != 18) return DTCWT_B200_EUNSUPPORTED;
+    if (tap_dot(h2_a, h2_b, m) > 0) return DTCWT_B200_EUNSUPPORTED;
+    Fwd2dArgs a;
+    const int rc = fwd_common(a, x, yh, yh, n, rows, cols, pad_r, pad_r, pad_c, pad_c, 2, 4, zs_n, zs_band, zs_row);
+    if (rc) return rc;
+    taps_dec(a.h1s, h2_a, h2_b, m, false, kInvSqrt2);
+    taps_dec(a.v1, h2_a, h2_b, m, false, 1.0);
+    a.h0 = a.h1s; a.v0 = a.v1; a.v1s = a.h1s;
+    for (int k = 0; k <= kStreamMaxTaps; ++k) {          // the packed row pass pairs a lowpass phase with a highpass one: h2 in both
+        a.ph0.p[k].x = 0.f;
+        a.ph0.p[k].y = (k < m) ? a.h1s.t[1][k] : 0.f;
+        a.ph1s.p[k].x = 0.f;
+        a.ph1s.p[k].y = (k < m) ? a.h1s.t[0][k] : 0.f;
+    }
+    if (m == 10) return launch_fwd2d<FwdLqHH<10>::type>(a, stream);
+    if (m == 14) return launch_fwd2d<FwdLqHH<14>::type>(a, stream);
+    return launch_fwd2d<FwdLqHH<18>::type>(a, stream);
+}
 #endif  // DTCWT_EMIT_FWD2D
 
 #ifdef DTCWT_EMIT_INV2D_Q
@@ -318,6 +368,28 @@ int dtcwt_b200_inv2d_levelq_f32(const float* z, const float* yh, float* out, int
     if (m == 14) return launch_inv2d<InvLq<14>::type>(a, stream);
     if (m == 16) return launch_inv2d<InvLq<16>::type>(a, stream);
     return launch_inv2d<InvLq<18>::type>(a, stream);
+}
+// transform2d.py:254-262 (`_bp`): out += H:g2(V:g2(c2q(bands 1, 4))); (g2_a, g2_b) are colifilt's (ha, hb), i.e. the reference
+// passes (g2b, g2a).  gain[6] is the level's gain_mask column (entries 1 and 4 are used).  Call AFTER
+// dtcwt_b200_inv2d_levelq_f32 with gain[1] = gain[4] = 0 on the same out.
+int dtcwt_b200_inv2d_levelq_hh_f32(const float* yh, float* out, int64_t n, int64_t rows, int64_t cols, int crop_r, int crop_c,
+                                   const double* g2_a, const double* g2_b, int m, const double* gain, int64_t zs_n, int64_t zs_band,
+                                   int64_t zs_row, void* stream) {
+    if (!g2_a || !g2_b || m < 2 || (m & 1)) return DTCWT_B200_EINVAL;
+    if (m != 10 && m != 14 && m != 18) return DTCWT_B200_EUNSUPPORTED;
+    if (tap_dot(g2_a, g2_b, m) > 0) return DTCWT_B200_EUNSUPPORTED;
+    if (!gain) return DTCWT_B200_EINVAL;
+    const double g[6] = {0.0, gain[1], 0.0, 0.0, gain[4], 0.0};
+    Inv2dArgs a;
+    const int rc = inv_common(a, out, yh, out, n, rows, cols, crop_r, crop_c, 4, 2, g, zs_n, zs_band, zs_row);   // the lowpass pointer is never used for data
+    if (rc) return rc;
+    a.out_vec4 = 0;
+    if (cols >= (1 << 27) || zs_row >= (1 << 27)) return DTCWT_B200_EUNSUPPORTED;
+    clear_taps(a.g0);
+    taps_int(a.g1, g2_a, g2_b, m, false);
+    if (m == 10) return launch_inv2d<InvLqHH<10>::type>(a, stream);
+    if (m == 14) return launch_inv2d<InvLqHH<14>::type>(a, stream);
+    return launch_inv2d<InvLqHH<18>::type>(a, stream);
 }
 #endif  // DTCWT_EMIT_INV2D_Q
 
@@ -393,6 +465,30 @@ int dtcwt_b200_inv2d_level1_f32(const float* z, const float* yh, float* out, int
     return launch_invs1<InvL1_19_19>(a, stream);
 }
 
+// transform2d.py:279-292 (`_bp`): out += H:g2o(V:g2o(c2q(bands 1, 4))).  Call AFTER dtcwt_b200_inv2d_level1_f32 with
+// gain[1] = gain[4] = 0 on the same out.
+int dtcwt_b200_inv2d_level1_hh_f32(const float* yh, float* out, int64_t n, int64_t rows, int64_t cols, const double* g2o, int m2,
+                                   const double* gain, int64_t zs_n, int64_t zs_band, int64_t zs_row, void* stream) {
+    if (!g2o || m2 < 1 || !gain) return DTCWT_B200_EINVAL;
+    if (!(m2 & 1) || m2 > 19) return DTCWT_B200_EUNSUPPORTED;
+    const double g[6] = {0.0, gain[1], 0.0, 0.0, gain[4], 0.0};
+    Inv2dArgs c;
+    const int rc = inv_common(c, out, yh, out, n, rows, cols, 0, 0, 1, 1, g, zs_n, zs_band, zs_row);
+    if (rc) return rc;
+    if (cols >= (1 << 27) || zs_row >= (1 << 27)) return DTCWT_B200_EUNSUPPORTED;
+    InvS1Args a;
+    a.z = out; a.yh = yh; a.out = out;                 // the lowpass pointer is only an address that may be read; its data is ignored
+    a.n = c.n; a.rows = c.rows; a.cols = c.cols;
+    a.out_vec4 = ((a.cols % 4) == 0 && aligned_to(out, 16)) ? 1 : 0;
+    a.zs_n = zs_n; a.zs_band = zs_band; a.zs_row = zs_row;
+    for (int b = 0; b < 6; ++b) a.gain[b] = c.gain[b];
+    for (int k = 0; k < kStreamMaxTaps; ++k) a.g0.t[k] = 0.f;
+    taps_col_s(a.g1, g2o, m2, 19, 1.0);
+    pair_tab(a.p0, a.g0, 19);
+    pair_tab(a.p1, a.g1, 19);
+    a.periods = choose_periods(a.rows, InvL1_hh::RING, (int64_t)InvL1_hh::tiles_c(a) * a.n);
+    return launch_invs1<InvL1_hh>(a, stream);
+}
 #endif  // DTCWT_EMIT_INV2D_1
 
 }  // extern "C"

@@ -230,7 +230,10 @@ struct Fwd2dArgs {
 //             families): the column pass gathers instead of scattering and forms the sums x[c-k] + x[c+k] once for BOTH
 //             filters, 8 FADD2 + 15 FFMA2 per output row pair instead of 28 FFMA2 for near_sym_b (the host checks the
 //             symmetry of the taps it is given bit for bit)
-constexpr int kFwdQ2c = 0, kFwdRaw = 1, kFwdLow = 2, kFwdSym = 3;
+//   kFwdHH    bands 1 and 4 only, from ONE filter in both directions: the band-pass filter h2 of the `_bp` families
+//             (transform2d.py:116-127, 145-157), passed in the H1 slot.  A `_bp` level is the ordinary launch followed by
+//             this one, which overwrites the two diagonal sub-bands.
+constexpr int kFwdQ2c = 0, kFwdRaw = 1, kFwdLow = 2, kFwdSym = 3, kFwdHH = 4;
 
 template <class H0, class H1, int GH_, int GW_, int NGV_, class TV0 = RtPhase, class TV1S = RtPhase, class TV1 = RtPhase,
           int MODE_ = kFwdQ2c>
@@ -346,13 +349,13 @@ struct Fwd2d {
 #pragma unroll
             for (int c = 0; c < WN / 4; ++c) {
                 const F4 v = src[c];
-                pair_gather4<H0::K, H0::MASK, C0, -HLA, 4, WN>(4 * c, v, a.ph0, oa);
+                if (MODE != kFwdHH) pair_gather4<H0::K, H0::MASK, C0, -HLA, 4, WN>(4 * c, v, a.ph0, oa);
                 if (MODE != kFwdLow) pair_gather4<H1::K, H1::MASK, C1, -HLA, 4, WN>(4 * c, v, a.ph1s, ob);
             }
             F4 va, vb;
             va.x = oa[0].x; va.y = oa[0].y; va.z = oa[1].x; va.w = oa[1].y;
             vb.x = ob[0].x; vb.y = ob[0].y; vb.z = ob[1].x; vb.w = ob[1].y;
-            *reinterpret_cast<F4*>(As + lr * CA + seg * 4) = va;
+            if (MODE != kFwdHH) *reinterpret_cast<F4*>(As + lr * CA + seg * 4) = va;
             if (MODE != kFwdLow) *reinterpret_cast<F4*>(Bs + lr * CA + seg * 4) = vb;
         }
     }
@@ -583,8 +586,36 @@ struct Fwd2d {
         *reinterpret_cast<F2*>(z1) = w1;
     }
 
+    // kFwdHH: V:h2 of B = H:h2(X)/sqrt2 -> q2c -> bands 1, 4
+    static DTCWT_D void phase_cols_hh(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        const float* Bs = sm + RX * CX + RX * CA;
+        constexpr int NCP = P * GW / 2;
+        for (int task = tid; task < NCP * (GH / NGV); task += kThreads) {
+            const int strip = task / NCP, cp = task - strip * NCP;
+            const int lrow = Q * NGV * strip;
+            const int orow = P * (GH * by + NGV * strip);
+            const int ocol = P * GW * bx + 2 * cp;
+            const int nrow = (ocol < a.out_cols) ? a.out_rows - orow : 0;
+            float* zb = a.yh + 2 * ((int64_t)bz * a.zs_n + (int64_t)(orow / 2) * a.zs_row + ocol / 2);
+            const int64_t bs = 2 * a.zs_band, rs = 2 * a.zs_row;
+            F2 hi[NOUT];
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i) hi[i] = zero2();
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                const F2 v = *reinterpret_cast<const F2*>(Bs + (lrow + j) * CA + 2 * cp);
+                fir_scatter<H1, NGV, HL, TV1>(j, v, a.v1, hi);
+            }
+            store_q2c(hi, zb + 1 * bs, zb + 4 * bs, rs, nrow / 2);
+        }
+    }
+
     // phase 4: column pass, one task = 2 adjacent columns x NGV groups of rows; results leave from registers
     static DTCWT_D void phase_cols(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        if (MODE == kFwdHH) {
+            phase_cols_hh(a, sm, bx, by, bz, tid);
+            return;
+        }
         if (MODE == kFwdSym) {
             phase_cols_sym(a, sm, bx, by, bz, tid);
             return;
@@ -670,10 +701,12 @@ struct Inv2dArgs {
 // without the symmetric-extension logic.
 // RAW (3-D transform, y/x passes of one slice, transform3d.py:485-490): the inputs are the four REAL images
 // s0..s3 of Fwd2d's kFwdRaw mode, image s at z + s * zs_band (floats), instead of lowpass + complex sub-bands.
-template <class G0, class G1, int NGV_, int NSTRIP_, int NWIDE_, bool RAW_ = false>
+// HH (`_bp` families, transform2d.py:254-262): the second launch of a level -- the lowpass counts as zero and the result is
+// ADDED to `out`; with the gains of the other four sub-bands zero and g2 in the G1 slot that is H:g2(V:g2(c2q(bands 1, 4))).
+template <class G0, class G1, int NGV_, int NSTRIP_, int NWIDE_, bool RAW_ = false, bool HH_ = false>
 struct Inv2d {
     typedef Inv2dArgs Args;
-    static constexpr bool RAW = RAW_;
+    static constexpr bool RAW = RAW_, HH = HH_;
     static constexpr int P = G0::P, Q = G0::Q;
     static constexpr int NGV = NGV_, NSTRIP = NSTRIP_, NWIDE = NWIDE_;
     static constexpr int NGH = 4 / Q;
@@ -783,6 +816,7 @@ struct Inv2d {
                 at = cur.v[0]; ab = cur.v[1]; bt = cur.v[2]; bb = cur.v[3];
             } else if (ROLE == 0) {
                 at = cur.v[0]; ab = cur.v[1];
+                if (HH) { at = zero2(); ab = zero2(); }
                 c2q_rows(cur.v[2], cur.v[3], ga0, ga1, bt, bb);
             } else {
                 c2q_rows(cur.v[0], cur.v[1], ga0, ga1, at, ab);
@@ -857,6 +891,11 @@ struct Inv2d {
             }
             const int c0 = (P / Q) * (TWI * bx + 4 * seg) - a.crop_c;     // first output column of the task
             float* d = img + (int64_t)r * a.out_cols + c0;
+            if (HH) {
+#pragma unroll
+                for (int i = 0; i < P * NGH; ++i)
+                    if (c0 + i >= 0 && c0 + i < a.out_cols) acc[i] += d[i];
+            }
             if (a.out_vec4 && c0 + P * NGH <= a.out_cols) {                // 16-byte aligned rows, no crop
 #pragma unroll
                 for (int c = 0; c < (P * NGH) / 4; ++c) {

@@ -85,7 +85,9 @@ struct InvS1Args {
 };
 
 // DBG (diagnosis builds only, results are wrong): 1 = memory traffic without the arithmetic, 2 = arithmetic without the loads
-template <int K0, int K1, uint32_t M0, uint32_t M1, int RING_, int NST_, class T0 = ArgTaps, class T1 = ArgTaps, int MINB_ = 2, int DBG = 0>
+// HH: the second launch of a `_bp` level (transform2d.py:279-292): lowpass counted as zero, result ADDED to `out`
+template <int K0, int K1, uint32_t M0, uint32_t M1, int RING_, int NST_, class T0 = ArgTaps, class T1 = ArgTaps, int MINB_ = 2, int DBG = 0,
+          bool HH = false>
 struct InvS1 {
     typedef InvS1Args Args;
     static constexpr int RING = RING_, PER = RING_ / 2, NST = NST_;
@@ -197,6 +199,7 @@ struct InvS1 {
             F2 at, ab, bt, bb;         // image A (filtered with g0) and image B (g1): top / bottom real rows
             if (ROLE == 0) {
                 at = cur.v[0]; ab = cur.v[1];
+                if (HH) { at = zero2(); ab = zero2(); }
                 c2q_rows(cur.v[2], cur.v[3], ga0, ga1, bt, bb);
             } else {
                 c2q_rows(cur.v[0], cur.v[1], ga0, ga1, at, ab);
@@ -276,6 +279,11 @@ struct InvS1 {
                     pair_gather4<K1, M1, C1, WS1 - CQ, 8, WE1 - WS1>(4 * c, s2[c], a.p1, acc);
             }
             float* d = img + (int64_t)r * a.cols + c0;
+            if (HH) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (c0 + 2 * i < a.cols) { const F2 o = *reinterpret_cast<const F2*>(d + 2 * i); acc[i].x += o.x; acc[i].y += o.y; }
+            }
             if (a.out_vec4 && c0 + 8 <= a.cols) {
                 F4 v;
                 v.x = acc[0].x; v.y = acc[0].y; v.z = acc[1].x; v.w = acc[1].y;

@@ -252,9 +252,10 @@ class Transform2d(object):
     def _fwd_level1(self, X, t, ph, pw, internal=False):
         """Level 1 (reference :112-130): undecimated biort filters, vertical axis first."""
         N = X.shape[0]
-        if t["h2o"] is None:
-            fused = _ops.fwd2d_level1(X, t["h0o"], t["h1o"], (ph, pw), internal)
-            if fused is not None:
+        fused = _ops.fwd2d_level1(X, t["h0o"], t["h1o"], (ph, pw), internal)
+        if fused is not None:
+            # `_bp` families (reference :116-121): a second launch overwrites the diagonal sub-bands with the band-pass ones
+            if t["h2o"] is None or _ops.fwd2d_level1_hh(X, fused[1], t["h2o"], (ph, pw)):
                 return fused
         Lo = _ops.colfilter(X, t["h0o"], 1, (0, ph))
         Hi = _ops.colfilter(X, t["h1o"], 1, (0, ph))
@@ -274,9 +275,9 @@ class Transform2d(object):
         N, r, c = LoLo.shape
         pr = (1, 1) if r % 4 else (0, 0)
         pc = (1, 1) if c % 4 else (0, 0)
-        if t["h2a"] is None:
-            fused = _ops.fwd2d_levelq(LoLo, t["h0b"], t["h0a"], t["h1b"], t["h1a"], (pr[0], pc[0]), internal)
-            if fused is not None:
+        fused = _ops.fwd2d_levelq(LoLo, t["h0b"], t["h0a"], t["h1b"], t["h1a"], (pr[0], pc[0]), internal)
+        if fused is not None:
+            if t["h2a"] is None or _ops.fwd2d_levelq_hh(LoLo, fused[1], t["h2b"], t["h2a"], (pr[0], pc[0])):       # reference :145-157
                 return fused
         Lo = _ops.coldfilt(LoLo, t["h0b"], t["h0a"], 1, pr)
         Hi = _ops.coldfilt(LoLo, t["h1b"], t["h1a"], 1, pr)
@@ -328,6 +329,13 @@ class Transform2d(object):
             fused = _ops.inv2d_levelq(Z, yh, t["g0b"], t["g0a"], t["g1b"], t["g1a"], g, (cr, cc))
             if fused is not None:
                 return fused
+        else:
+            # `_bp` (reference :254-262): the ordinary launch without the diagonal sub-bands, then out += their g2 contribution
+            g_rest = np.array(g, dtype=np.float64)
+            g_rest[[1, 4]] = 0.0
+            fused = _ops.inv2d_levelq(Z, yh, t["g0b"], t["g0a"], t["g1b"], t["g1a"], g_rest, (cr, cc))
+            if fused is not None and _ops.inv2d_levelq_hh(yh, fused, Z.shape[1], Z.shape[2], t["g2b"], t["g2a"], g, (cr, cc)):
+                return fused
         lh = _ops.c2q(yh, _BANDS_HL[0], _BANDS_HL[1], g[0], g[5])
         hl = _ops.c2q(yh, _BANDS_LH[0], _BANDS_LH[1], g[2], g[3])
         hh = _ops.c2q(yh, _BANDS_HH[0], _BANDS_HH[1], g[1], g[4])
@@ -349,6 +357,12 @@ class Transform2d(object):
         if t["g2o"] is None:
             fused = _ops.inv2d_level1(Z, yh, t["g0o"], t["g1o"], g)
             if fused is not None:
+                return fused
+        else:
+            g_rest = np.array(g, dtype=np.float64)
+            g_rest[[1, 4]] = 0.0
+            fused = _ops.inv2d_level1(Z, yh, t["g0o"], t["g1o"], g_rest)
+            if fused is not None and _ops.inv2d_level1_hh(yh, fused, t["g2o"], g):          # reference :279-292
                 return fused
         lh = _ops.c2q(yh, _BANDS_HL[0], _BANDS_HL[1], g[0], g[5])
         hl = _ops.c2q(yh, _BANDS_LH[0], _BANDS_LH[1], g[2], g[3])

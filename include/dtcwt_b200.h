@@ -177,6 +177,25 @@ int dtcwt_b200_inv2d_levelq_f32(const float *z, const float *yh, float *out, int
 int dtcwt_b200_inv2d_level1_f32(const float *z, const float *yh, float *out, int64_t n, int64_t rows, int64_t cols,
                                 const double *g0o, int m0, const double *g1o, int m1, const double *gain,
                                 int64_t zs_n, int64_t zs_band, int64_t zs_row, void *stream);
+/* `_bp` families (6-tuple biort, 12-tuple qshift; transform2d.py:116-127, 145-157, 254-262, 279-292): the diagonal
+ * sub-bands 1 and 4 use the band-pass pair h2 / g2 in both directions.  A `_bp` level is the ordinary launch above
+ * followed by one of these on the same yh / out:
+ *   fwd2d_level*_hh  overwrite bands 1 and 4 of yh with q2c(V:h2(H:h2(x)))
+ *   inv2d_level*_hh  out += H:g2(V:g2(c2q(bands 1, 4) * gain[1], gain[4])); the ordinary inverse launch before it is given
+ *                    gain[1] = gain[4] = 0
+ * (h2_a, h2_b) / (g2_a, g2_b) are coldfilt's / colifilt's (ha, hb): the reference passes (h2b, h2a) / (g2b, g2a). */
+int dtcwt_b200_fwd2d_level1_hh_f32(const float *x, float *yh, int64_t n, int64_t rows, int64_t cols, int pad_r_hi,
+                                   int pad_c_hi, const double *h2o, int m2, int64_t zs_n, int64_t zs_band,
+                                   int64_t zs_row, void *stream);
+int dtcwt_b200_fwd2d_levelq_hh_f32(const float *x, float *yh, int64_t n, int64_t rows, int64_t cols, int pad_r, int pad_c,
+                                   const double *h2_a, const double *h2_b, int m, int64_t zs_n, int64_t zs_band,
+                                   int64_t zs_row, void *stream);
+int dtcwt_b200_inv2d_levelq_hh_f32(const float *yh, float *out, int64_t n, int64_t rows, int64_t cols, int crop_r,
+                                   int crop_c, const double *g2_a, const double *g2_b, int m, const double *gain,
+                                   int64_t zs_n, int64_t zs_band, int64_t zs_row, void *stream);
+int dtcwt_b200_inv2d_level1_hh_f32(const float *yh, float *out, int64_t n, int64_t rows, int64_t cols, const double *g2o,
+                                   int m2, const double *gain, int64_t zs_n, int64_t zs_band, int64_t zs_row,
+                                   void *stream);
 
 /* ---- fused per-level 3-D transform (float32) -----------------------------------
  * A level of Transform3d is two launches: the two in-slice axes of every slice in one

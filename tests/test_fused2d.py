@@ -138,11 +138,11 @@ def test_fused_wavelet_families(backend, biort, qshift):
 
 
 def test_fused_unsupported_falls_back_to_generic_kernels(backend):
-    """qshift_32 has 32 taps (no fused instance), near_sym_b_bp is a 6-tuple biort, 24x24 is below the fused
-    minimum: the generic CUDA kernels must produce the result instead."""
+    """qshift_32 has 32 taps (no fused instance), 24x24 is below the fused minimum: the generic CUDA kernels must produce
+    the result instead."""
     rs = np.random.RandomState(3)
     X = rs.rand(64, 64).astype(np.float32)
-    for biort, qshift in (("near_sym_b", "qshift_32"), ("near_sym_b_bp", "qshift_b_bp")):
+    for biort, qshift in (("near_sym_b", "qshift_32"),):
         xf = dtcwt_b200.Transform2d(biort, qshift)
         to = O.Transform2d(coeffs.biort(biort), coeffs.qshift(qshift))
         with Launches() as L:
@@ -154,6 +154,29 @@ def test_fused_unsupported_falls_back_to_generic_kernels(backend):
     with Launches() as L:
         dtcwt_b200.Transform2d("near_sym_b", "qshift_b").forward(X[:24, :24], 1)
     assert any("colfilter" in n for n in L.names)
+
+
+def test_fused_bp_families(backend):
+    """near_sym_b_bp / qshift_b_bp (6- and 12-tuples, reference transform2d.py:116-127, 145-157, 254-262, 279-292): every
+    level is two fused launches -- the ordinary one and the band-pass one for sub-bands 1 and 4 -- nothing else."""
+    rs = np.random.RandomState(29)
+    X = rs.rand(2, 264, 256).astype(np.float32)
+    xf = dtcwt_b200.Transform2d("near_sym_b_bp", "qshift_b_bp")
+    to = O.Transform2d(coeffs.biort("near_sym_b_bp"), coeffs.qshift("qshift_b_bp"))
+    gm = rs.rand(6, 3)
+    with Launches() as L:
+        p = xf.forward_channels(X, "nhw", 3)
+        Z = npy(xf.inverse_channels(p, "nhw"))
+        Zg = npy(xf.inverse_channels(p, "nhw", gm))
+    assert L.only_fused(), L.names
+    assert sum(n.endswith("_hh_f32") for n in L.names) == 9 and len(L.names) == 18
+    for i in range(2):
+        po = to.forward(X[i], 3)
+        assert rel_err(p.lowpass[i], po.lowpass) < REL_TOL
+        for a, b in zip(p.highpasses, po.highpasses):
+            assert rel_err(a[i], b) < REL_TOL
+        assert rel_err(Zg[i], to.inverse(po, gm)) < REL_TOL
+        assert rel_err(Z[i], to.inverse(po)) < REL_TOL      # (the band-pass families are not a perfect-reconstruction set)
 
 
 def test_fused_16_tap_qshift(backend):
