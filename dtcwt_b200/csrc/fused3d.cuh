@@ -178,33 +178,39 @@ struct Z3Inv {
         o.v[1][1].y = -p.y + q.y + r.y - s.y;       // H
     }
 
-    template <bool INSIDE>
+    // the octets (lowpass-in-depth, highpass-in-depth) of logical octet index o, mirrored into the volume; flip: the mirror
+    // exchanges the two axis-0 parities
+    static DTCWT_D void fetch(const Args& a, int sub, int b, int yp, int xp, int o, int noct, int64_t plane, int t1, int t2,
+                              Oct& lo, Oct& hi, bool& flip) {
+        int oz = o;
+        flip = false;
+        if (oz < 0) { oz = -1 - oz; flip = true; } else if (oz >= noct) { oz = 2 * noct - 1 - oz; flip = true; }
+        oz = oz < 0 ? 0 : (oz >= noct ? noct - 1 : oz);         // further out only feeds outputs that are never stored
+        if (sub == 0) {
+            const float* p = a.s + ((int64_t)b * a.d0 + 2 * oz) * plane + (int64_t)(2 * yp) * a.w + 2 * xp;
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+                    const F2 v = *reinterpret_cast<const F2*>(p + (int64_t)e * plane + (int64_t)f * a.w);
+                    lo.v[e][f].x = 2.f * v.x; lo.v[e][f].y = 2.f * v.y;
+                }
+        } else {
+            unpack(a, octant_block(0, t1, t2), b, oz, yp, xp, lo);
+        }
+        unpack(a, octant_block(1, t1, t2), b, oz, yp, xp, hi);
+    }
+
+    // (Variants of this loop that did not pay, profiles/r2_02: a second copy without the mirror logic for interior windows,
+    // 1.10 vs 0.99 ms per step; loading octet jq + 1 before scattering octet jq, 96 registers / 2 CTAs per SM, 1.03 ms.)
     static DTCWT_D void accumulate(const Args& a, F2 (&acc)[2][NOUT], int sub, int b, int yp, int xp, int o0, int noct, int64_t plane,
                                    int t1, int t2) {
 #pragma unroll
         for (int jq = 0; jq < NR / 2; ++jq) {
-            // symmetric extension at octet granularity: a mirrored octet has its axis-0 parities exchanged
-            int oz = o0 + jq;
-            bool flip = false;
-            if (!INSIDE) {
-                if (oz < 0) { oz = -1 - oz; flip = true; } else if (oz >= noct) { oz = 2 * noct - 1 - oz; flip = true; }
-                oz = oz < 0 ? 0 : (oz >= noct ? noct - 1 : oz);     // further out only feeds outputs that are never stored
-            }
             Oct lo, hi;
-            if (sub == 0) {
-                const float* p = a.s + ((int64_t)b * a.d0 + 2 * oz) * plane + (int64_t)(2 * yp) * a.w + 2 * xp;
-#pragma unroll
-                for (int e = 0; e < 2; ++e)
-#pragma unroll
-                    for (int f = 0; f < 2; ++f) {
-                        const F2 v = *reinterpret_cast<const F2*>(p + (int64_t)e * plane + (int64_t)f * a.w);
-                        lo.v[e][f].x = 2.f * v.x; lo.v[e][f].y = 2.f * v.y;
-                    }
-            } else {
-                unpack(a, octant_block(0, t1, t2), b, oz, yp, xp, lo);
-            }
-            unpack(a, octant_block(1, t1, t2), b, oz, yp, xp, hi);
-            if (!INSIDE && flip) {                                          // selects, not indexed: the octets stay in registers
+            bool flip;
+            fetch(a, sub, b, yp, xp, o0 + jq, noct, plane, t1, t2, lo, hi, flip);
+            if (flip) {                                          // selects, not indexed: the octets stay in registers
 #pragma unroll
                 for (int f = 0; f < 2; ++f) {
                     F2 t = lo.v[0][f]; lo.v[0][f] = lo.v[1][f]; lo.v[1][f] = t;
@@ -240,9 +246,7 @@ struct Z3Inv {
 #pragma unroll
         for (int i = 0; i < NOUT; ++i) { acc[0][i] = zero2(); acc[1][i] = zero2(); }
         const int o0 = (Q * NG * gz - HL) / 2;                   // first octet along axis 0 (may be negative)
-        // (a copy of this loop without the mirror logic for interior windows measured SLOWER here -- 1.10 vs 0.99 ms per step,
-        // profiles/r2_05 -- unlike in the forward pass, where it removed a modulo per slice; one instantiation only)
-        accumulate<false>(a, acc, sub, b, yp, xp, o0, noct, plane, t1, t2);
+        accumulate(a, acc, sub, b, yp, xp, o0, noct, plane, t1, t2);
         float* d = a.lll + sub * a.sub_stride + b * a.vol_stride + (int64_t)(2 * yp) * a.w + 2 * xp;
 #pragma unroll
         for (int i = 0; i < NOUT; ++i) {
