@@ -312,12 +312,11 @@ struct Fwd2d {
         int n_lo, hi0;
         outside_range(L0, RX, a.pr_lo, a.rows, n_lo, hi0);
         const int n_out = n_lo + (RX - hi0);
-        // one outside row per iteration: its source row is found once (uniform over the CTA), the threads copy along it
-        for (int k = 0; k < n_out; ++k) {
+        for (int e = tid; e < n_out * CX; e += kThreads) {
+            const int k = e / CX, lc = e - k * CX;
             const int lr = k < n_lo ? k : hi0 + (k - n_lo);
             const int src = mirror_src(L0 + lr, a.Lr, a.pr_lo, a.rows, L0, RX);
-            if (src >= 0)
-                for (int lc = tid; lc < CX; lc += kThreads) sm[lr * CX + lc] = sm[src * CX + lc];
+            if (src >= 0) sm[lr * CX + lc] = sm[src * CX + lc];
         }
     }
     static DTCWT_D void phase_patch_cols(const Args& a, float* sm, int bx, int by, int bz, int tid) {
@@ -326,11 +325,12 @@ struct Fwd2d {
         int n_lo, hi0;
         outside_range(L0, CX, a.pc_lo, a.cols, n_lo, hi0);
         const int n_out = n_lo + (CX - hi0);
-        for (int k = 0; k < n_out; ++k) {                        // one outside column per iteration, the threads copy down it
+        if (n_out == 0) return;
+        for (int e = tid; e < RX * n_out; e += kThreads) {
+            const int lr = e / n_out, k = e - lr * n_out;
             const int lc = k < n_lo ? k : hi0 + (k - n_lo);
             const int src = mirror_src(L0 + lc, a.Lc, a.pc_lo, a.cols, L0, CX);
-            if (src >= 0)
-                for (int lr = tid; lr < RX; lr += kThreads) sm[lr * CX + lc] = sm[lr * CX + src];
+            if (src >= 0) sm[lr * CX + lc] = sm[lr * CX + src];
         }
     }
 
