@@ -43,6 +43,32 @@ __global__ void __launch_bounds__(kFusedThreads, K::kMinBlocks)
 fwd2d_kernel(const __grid_constant__ typename K::Args a, const __grid_constant__ CUtensorMap tmap) {
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
+    if (!K::kPersistent) {
+        // one CTA per tile on a 3-D grid: the tile coordinates are the block indices -- no integer divisions in front of
+        // the TMA issue (they were 10 % of the level-1 kernel's stall samples, profiles/r2_04)
+        const int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
+        if (a.use_tma) {
+            if (tid == 0) {
+                mbar_init(&bar, 1);
+                fence_mbar_init();
+                mbar_expect_tx(&bar, (uint32_t)(K::RX * K::CX * sizeof(float)));
+                tma_load_3d(fused_smem, &tmap, K::col0(bx) - a.pc_lo, K::row0(by) - a.pr_lo, bz, &bar);
+            }
+            __syncthreads();
+            mbar_wait(&bar, 0);
+        } else {
+            K::template phase<0>(a, fused_smem, bx, by, bz, tid);
+        }
+        __syncthreads();
+        K::template phase<1>(a, fused_smem, bx, by, bz, tid);
+        __syncthreads();
+        K::template phase<2>(a, fused_smem, bx, by, bz, tid);
+        __syncthreads();
+        K::template phase<3>(a, fused_smem, bx, by, bz, tid);
+        __syncthreads();
+        K::template phase<4>(a, fused_smem, bx, by, bz, tid);
+        return;
+    }
     const int tc = K::tiles_c(a), tr = K::tiles_r(a);
     const int ntiles = tc * tr * a.n;
     if (a.use_tma) {
@@ -260,8 +286,14 @@ static int launch_fwd2d(typename K::Args& a, void* stream) {
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fwd2d_kernel<K>, kFusedThreads, smem)) != cudaSuccess)
         return (int)e;
+    if (!K::kPersistent) {
+        if (K::tiles_r(a) > 65535 || a.n > 65535) return DTCWT_B200_EUNSUPPORTED;      // grid.y / grid.z limits
+        const dim3 grid((unsigned)K::tiles_c(a), (unsigned)K::tiles_r(a), (unsigned)a.n);
+        fwd2d_kernel<K><<<grid, kFusedThreads, smem, (cudaStream_t)stream>>>(a, map);
+        return (int)cudaGetLastError();
+    }
     int64_t ctas = (int64_t)sms * (per_sm > 0 ? per_sm : 1);          // one wave of resident CTAs, each walks over tiles
-    if (ctas > ntiles || !K::kPersistent) ctas = ntiles;
+    if (ctas > ntiles) ctas = ntiles;
     fwd2d_kernel<K><<<(unsigned)ctas, kFusedThreads, smem, (cudaStream_t)stream>>>(a, map);
     return (int)cudaGetLastError();
 }
