@@ -360,8 +360,8 @@ class LaunchLog(object):
     def __init__(self, torch):
         self.torch, self.count, self.events, self.timing, self.only = torch, 0, [], False, None
 
-    def __call__(self, symbol, thunk):
-        self.count += 1
+    def __call__(self, symbol, thunk, launches=1):
+        self.count += launches
         if not self.timing or (self.only is not None and symbol != self.only):
             thunk()
             return

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdtcwt_b200.so")
 
 _LIB = None
-ABI_VERSION = 200       # DTCWT_B200_VERSION of include/dtcwt_b200.h this binding was written against
+ABI_VERSION = 201       # DTCWT_B200_VERSION of include/dtcwt_b200.h this binding was written against
 
 _P, _I, _L, _D = c_void_p, c_int, c_int64, c_double
 _TAPS = ctypes.POINTER(c_double)
@@ -36,6 +36,7 @@ _TYPED = {
     "sample": [_P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _I, _TAPS, _TAPS, _P],
 }
 _UNTYPED = {
+    "l2_info": [ctypes.POINTER(c_int64)],
     "reg_boxrescale": [_P, _P, _L, _L, _L, _L, _L, _I, _P],
     "reg_solve": [_P, _P, _L, _I, _P],
     "reg_coords": [_P, _P, _P, _L, _L, _L, _L, _L, _I, _P],
@@ -50,6 +51,10 @@ _F32_ONLY = {
     "fwd2d_levelq_hh": [_P, _P, _L, _L, _L, _I, _I, _TAPS, _TAPS, _I, _L, _L, _L, _P],
     "inv2d_levelq_hh": [_P, _P, _L, _L, _L, _I, _I, _TAPS, _TAPS, _I, _TAPS, _L, _L, _L, _P],
     "inv2d_level1_hh": [_P, _P, _L, _L, _L, _TAPS, _I, _TAPS, _L, _L, _L, _P],
+    "fwd2d_level12": [_P, _P, _P, _P, _P, _L, _L, _L, _I, _I, _TAPS, _I, _TAPS, _I, _TAPS, _TAPS, _TAPS, _TAPS, _I,
+                      _L, _L, _L, _L, _L, _L, _L, _I, _P],
+    "inv2d_level21": [_P, _P, _P, _P, _P, _L, _L, _L, _I, _I, _TAPS, _TAPS, _TAPS, _TAPS, _I, _TAPS, _TAPS, _I, _TAPS, _I,
+                      _TAPS, _L, _L, _L, _L, _L, _L, _L, _I, _P],
     "fwd3d_level1_lo": [_P, _P, _P, _L, _L, _L, _L, _TAPS, _I, _P],
     "inv3d_level1_lo": [_P, _P, _P, _L, _L, _L, _L, _TAPS, _I, _P],
     "fwd3d_level1": [_P, _P, _P, _P, _L, _L, _L, _L, _TAPS, _I, _TAPS, _I, _L, _L, _L, _L, _L, _P],
@@ -126,9 +131,10 @@ def set_launch_hook(hook):
 E_UNSUPPORTED = -2
 
 
-def call_optional(name, dtype_suffix, *args):
+def call_optional(name, dtype_suffix, *args, launches=1):
     """Like :func:`call`, but a DTCWT_B200_EUNSUPPORTED answer returns False (nothing was launched)
-    so the caller can compose the same result from the generic CUDA kernels."""
+    so the caller can compose the same result from the generic CUDA kernels.  launches: kernel launches the
+    entry point makes (the chained entry points make two per chunk), reported to the launch hook."""
     symbol = "dtcwt_b200_%s_%s" % (name, dtype_suffix)
     fn = getattr(lib(), symbol)
     out = []
@@ -141,8 +147,10 @@ def call_optional(name, dtype_suffix, *args):
 
     if _LAUNCH_HOOK is None:
         thunk()
-    else:
+    elif launches == 1:
         _LAUNCH_HOOK(symbol, thunk)
+    else:
+        _LAUNCH_HOOK(symbol, thunk, launches)
     return out[0] == 0
 
 

@@ -8,6 +8,7 @@ PyTorch is used for device memory and streams only.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -267,6 +268,89 @@ def fwd2d_levelq(x, lo_a, lo_b, hi_a, hi_b, pad, internal=None):
                                 taps[0][1], taps[1][1], taps[2][1], taps[3][1], taps[0][2],
                                 yh.stride(0), yh.stride(1), yh.stride(2), _stream(x))
     return (lolo, yh) if ok else None
+
+
+def chain_mode():
+    """How levels 1 and 2 of a batched 2-D transform are launched: 0 = one launch per level over the whole batch;
+    1..100 = chained chunk by chunk with the level-1 lowpass L2-persisting (hit ratio in percent); -1 = chained
+    without the cache policy.  DTCWT_B200_CHAIN overrides the default (read per call: an experiment switch)."""
+    try:
+        return int(os.environ.get("DTCWT_B200_CHAIN", CHAIN_DEFAULT))
+    except ValueError:
+        return CHAIN_DEFAULT
+
+
+CHAIN_DEFAULT = 0
+CHAIN_BUDGET_MB = 64      # LoLo1 of one chunk: half of the B200's 126 MB L2
+
+
+def chain_chunk(n, rows, cols):
+    """Images per chunk of the chained levels (0: do not chain -- one image, or images too large for L2 / too small
+    to fill the GPU one chunk at a time)."""
+    budget = int(os.environ.get("DTCWT_B200_CHAIN_MB", CHAIN_BUDGET_MB)) << 20
+    min_pix = int(os.environ.get("DTCWT_B200_CHAIN_MIN_PIX", 1 << 20))      # tests chain small images
+    per = 4 * rows * cols
+    if n < 2 or per > budget or rows * cols < min_pix:
+        return 0
+    return max(1, min(n, budget // per))
+
+
+def fwd2d_level12(x, h0o, h1o, lo_a, lo_b, hi_a, hi_b, pad_hi, internal2=None):
+    """Levels 1 and 2 of the forward transform chained chunk by chunk (LoLo1 never returned): x [n][H][W] ->
+    (LoLo2, Yh1 planar, Yh2 planar), or None when not applicable (then the caller runs the levels one by one)."""
+    mode = chain_mode()
+    if mode == 0 or not _fused_ok(x):
+        return None
+    n, r, c = x.shape
+    Lr, Lc = r + pad_hi[0], c + pad_hi[1]
+    chunk = chain_chunk(n, Lr, Lc)
+    if chunk == 0:
+        return None
+    k0, p0, m0 = _taps(h0o)
+    k1, p1, m1 = _taps(h1o)
+    taps = [_taps(h) for h in (lo_a, lo_b, hi_a, hi_b)]
+    if len({t[2] for t in taps}) != 1:
+        return None
+    pr, pc = (1 if Lr % 4 else 0), (1 if Lc % 4 else 0)
+    r2, c2 = (Lr + 2 * pr) // 2, (Lc + 2 * pc) // 2
+    lolo1 = scratch("lolo1c", (chunk, Lr, Lc), x.dtype, x.device)
+    lolo2 = scratch(internal2, (n, r2, c2), x.dtype, x.device) if internal2 else torch.empty((n, r2, c2), dtype=x.dtype, device=x.device)
+    yh1 = new_highpass(n, 6, (Lr // 2, Lc // 2), x.dtype, x.device)
+    yh2 = new_highpass(n, 6, (r2 // 2, c2 // 2), x.dtype, x.device)
+    with _on_device(x):
+        ok = _lib.call_optional("fwd2d_level12", "f32", _ptr(x), _ptr(lolo1), _ptr(lolo2), _ptr(yh1), _ptr(yh2), n, r, c,
+                                pad_hi[0], pad_hi[1], p0, m0, p1, m1, taps[0][1], taps[1][1], taps[2][1], taps[3][1], taps[0][2],
+                                yh1.stride(0), yh1.stride(1), yh1.stride(2), yh2.stride(0), yh2.stride(1), yh2.stride(2),
+                                chunk, max(mode, 0), _stream(x), launches=2 * ((n + chunk - 1) // chunk))
+    return (lolo2, yh1, yh2) if ok else None
+
+
+def inv2d_level21(z2, yh2, yh1, lo_a, lo_b, hi_a, hi_b, gain2, g0o, g1o, gain1, crop):
+    """Levels 2 and 1 of the inverse transform chained chunk by chunk; None when not applicable."""
+    mode = chain_mode()
+    if mode == 0 or not _fused_ok(z2, yh2, yh1) or not yh2.is_contiguous() or not yh1.is_contiguous():
+        return None
+    n, r, c = z2.shape
+    r1, c1 = 2 * r - 2 * crop[0], 2 * c - 2 * crop[1]
+    chunk = chain_chunk(n, r1, c1)
+    if chunk == 0:
+        return None
+    taps = [_taps(h) for h in (lo_a, lo_b, hi_a, hi_b)]
+    if len({t[2] for t in taps}) != 1:
+        return None
+    k0, p0, m0 = _taps(g0o)
+    k1, p1, m1 = _taps(g1o)
+    g2k, g2p = _gain6(gain2)
+    g1k, g1p = _gain6(gain1)
+    z1 = scratch("z1c", (chunk, r1, c1), z2.dtype, z2.device)
+    out = torch.empty((n, r1, c1), dtype=z2.dtype, device=z2.device)
+    with _on_device(z2):
+        ok = _lib.call_optional("inv2d_level21", "f32", _ptr(z2), _ptr(yh2), _ptr(yh1), _ptr(z1), _ptr(out), n, r, c,
+                                crop[0], crop[1], taps[0][1], taps[1][1], taps[2][1], taps[3][1], taps[0][2], g2p,
+                                p0, m0, p1, m1, g1p, yh2.stride(0), yh2.stride(1), yh2.stride(2),
+                                yh1.stride(0), yh1.stride(1), yh1.stride(2), chunk, max(mode, 0), _stream(z2),
+                                launches=2 * ((n + chunk - 1) // chunk))
+    return out if ok else None
 
 
 def _gain6(gain):

@@ -92,6 +92,8 @@ typedef Fwd2d<SpecCol<13, kMask13>, SpecCol<19, kMask19>, 64, 64, 8, BakedPhase<
               BakedPhase<NearSymB_h1> > FwdT1_nsb;    // near_sym_b: exact-zero taps compiled out, column taps as immediates
 typedef Fwd2d<SpecCol<13, kMask13>, SpecCol<19, kMask19>, 64, 64, 8, BakedPhase<NearSymB_h0>, BakedPhase<NearSymB_h1s>,
               BakedPhase<NearSymB_h1>, kFwdSym> FwdT1_nsb_sym;    // the same, column pass with shared symmetric sums: the default (measured 5 % faster)
+typedef Fwd2d<SpecCol<13, kMask13>, SpecCol<19, kMask19>, 64, 64, 8, BakedPhase<NearSymB_h0>, BakedPhase<NearSymB_h1s>,
+              BakedPhase<NearSymB_h1>, kFwdSymP> FwdT1_nsb_symp;   // experiment: DTCWT_B200_FWD_PERSIST=1
 typedef Fwd2d<SpecCol<5>, SpecCol<7>, 64, 64, 8, RtPhase, RtPhase, RtPhase, kFwdSym> FwdT1_5_7_sym;
 typedef Fwd2d<SpecCol<19>, SpecCol<19>, 64, 64, 8, RtPhase, RtPhase, RtPhase, kFwdSym> FwdT1_19_19_sym;
 typedef Fwd2d<SpecCol<5>, SpecCol<7>, 64, 64, 8> FwdT1_5_7;                         // near_sym_a (+ legall 5/3)
@@ -221,6 +223,7 @@ int dtcwt_b200_fwd2d_level1_f32(const float* x, float* lolo, float* yh, int64_t 
         for (int k = 0; k < KT0 && sym; ++k) sym = c.v0.t[0][k] == c.v0.t[0][KT0 - 1 - k];
         for (int k = 0; k < K1 && sym; ++k) sym = c.v1.t[0][k] == c.v1.t[0][K1 - 1 - k] && c.v1s.t[0][k] == c.v1s.t[0][K1 - 1 - k];
         if (small) return sym ? launch_fwd2d<FwdT1_5_7_sym>(c, stream) : launch_fwd2d<FwdT1_5_7>(c, stream);
+        if (nsb && sym && env_int("DTCWT_B200_FWD_PERSIST", 0)) return launch_fwd2d<FwdT1_nsb_symp>(c, stream);
         if (nsb) return sym ? launch_fwd2d<FwdT1_nsb_sym>(c, stream) : launch_fwd2d<FwdT1_nsb>(c, stream);
         return sym ? launch_fwd2d<FwdT1_19_19_sym>(c, stream) : launch_fwd2d<FwdT1_19_19>(c, stream);
     }
@@ -267,6 +270,9 @@ int dtcwt_b200_fwd2d_levelq_f32(const float* x, float* lolo, float* yh, int64_t 
         if (v == 1) return launch_fwd2d<Fwd2d<SpecDec<14, true>, SpecDec<14, false>, 32, 16, 2> >(a, stream);
         if (v == 2) return launch_fwd2d<Fwd2d<SpecDec<14, true>, SpecDec<14, false>, 16, 16, 4> >(a, stream);
         if (v == 3) return launch_fwd2d<Fwd2d<SpecDec<14, true>, SpecDec<14, false>, 16, 16, 2> >(a, stream);
+        if (v == 5) return launch_fwd2d<Fwd2d<SpecDec<14, true>, SpecDec<14, false>, 20, 16, 4> >(a, stream);     // 71 KB: 3 CTAs per SM
+        if (v == 4)      // column tasks not split into A / B halves (half of the warps idle in the column pass)
+            return launch_fwd2d<Fwd2d<SpecDec<14, true>, SpecDec<14, false>, 32, 16, 4, RtPhase, RtPhase, RtPhase, kFwdQ2c, false> >(a, stream);
         return launch_fwd2d<FwdLq<14>::type>(a, stream);
     }
     if (m == 16) return launch_fwd2d<FwdLq<16>::type>(a, stream);

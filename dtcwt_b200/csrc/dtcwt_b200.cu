@@ -71,6 +71,7 @@ static int launch_z3(const Z3Args& a, void* stream) {
 #include "abi_fused2d.inl"
 #include "abi_axis.inl"
 #include "abi_fused3d.inl"
+#include "abi_chain.inl"
 
 #ifdef DTCWT_EMIT_GENERIC
 extern "C" {

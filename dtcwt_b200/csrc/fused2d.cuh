@@ -233,10 +233,11 @@ struct Fwd2dArgs {
 //   kFwdHH    bands 1 and 4 only, from ONE filter in both directions: the band-pass filter h2 of the `_bp` families
 //             (transform2d.py:116-127, 145-157), passed in the H1 slot.  A `_bp` level is the ordinary launch followed by
 //             this one, which overwrites the two diagonal sub-bands.
-constexpr int kFwdQ2c = 0, kFwdRaw = 1, kFwdLow = 2, kFwdSym = 3, kFwdHH = 4;
+//   kFwdSymP  kFwdSym as a persistent kernel (one resident wave of CTAs, next tile prefetched during the column pass): experiment
+constexpr int kFwdQ2c = 0, kFwdRaw = 1, kFwdLow = 2, kFwdSym = 3, kFwdHH = 4, kFwdSymP = 5;
 
 template <class H0, class H1, int GH_, int GW_, int NGV_, class TV0 = RtPhase, class TV1S = RtPhase, class TV1 = RtPhase,
-          int MODE_ = kFwdQ2c>
+          int MODE_ = kFwdQ2c, bool SPLIT_ = true>
 struct Fwd2d {
     typedef Fwd2dArgs Args;
     static constexpr int MODE = MODE_;
@@ -260,7 +261,7 @@ struct Fwd2d {
     static constexpr int kPhases = 5;
     // q-shift levels: one resident wave of CTAs walks over the tiles and prefetches the next tile during the column
     // pass (measured 4 % faster); level 1 is faster with one CTA per tile (profiles/r1_03)
-    static constexpr bool kPersistent = (P != 1);
+    static constexpr bool kPersistent = (P != 1) || (MODE_ == kFwdSymP);
     static constexpr int kMinBlocks = (kSmemFloats * 4 * 3 <= 220 * 1024) ? 3 : 2;      // CTAs per SM the shared memory allows
     static_assert(P == H1::P && Q == H1::Q, "filter pair must share its rate");
     static_assert((NOUT % 2) == 0 && (GH % NGV) == 0 && (GW % NGH) == 0 && (CA % 2) == 0, "tile shape");
@@ -476,19 +477,26 @@ struct Fwd2d {
             if (i < nrow) *reinterpret_cast<F2*>(dst + (int64_t)i * rs) = y[i];
     }
 
+    // Column tasks of a tile: NCP column pairs x GH / NGV strips.  The q-shift tiles have only half as many as the CTA has
+    // threads; there the A half (LoLo + bands 0, 5 / images s0, s1) and the B half (bands 2, 3 and 1, 4 / images s2, s3)
+    // of a task go to different warps, so every warp has work in the column pass (kSplitAB).
+    static constexpr int NTASK = (P * GW / 2) * (GH / NGV);
+    static constexpr bool kSplitAB = SPLIT_ && (2 * NTASK <= kThreads) && MODE_ != kFwdLow && MODE_ != kFwdHH;
+
     // column pass of the 3-D modes: real images out
-    static DTCWT_D void phase_cols_real(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+    template <bool DO_A, bool DO_B>
+    static DTCWT_D void cols_real_task(const Args& a, float* sm, int bx, int by, int bz, int task) {
         const float* As = sm + RX * CX;
         const float* Bs = As + RX * CA;
         constexpr int NCP = P * GW / 2;
-        for (int task = tid; task < NCP * (GH / NGV); task += kThreads) {
-            const int strip = task / NCP, cp = task - strip * NCP;
-            const int lrow = Q * NGV * strip;
-            const int orow = P * (GH * by + NGV * strip);
-            const int ocol = P * GW * bx + 2 * cp;
-            const int nrow = (ocol < a.out_cols) ? a.out_rows - orow : 0;
-            float* dst = a.lolo + ((int64_t)bz * a.out_rows + orow) * a.out_cols + ocol;
-            F2 lo[NOUT], hi[NOUT];
+        const int strip = task / NCP, cp = task - strip * NCP;
+        const int lrow = Q * NGV * strip;
+        const int orow = P * (GH * by + NGV * strip);
+        const int ocol = P * GW * bx + 2 * cp;
+        const int nrow = (ocol < a.out_cols) ? a.out_rows - orow : 0;
+        float* dst = a.lolo + ((int64_t)bz * a.out_rows + orow) * a.out_cols + ocol;
+        F2 lo[NOUT], hi[NOUT];
+        if (DO_A) {
 #pragma unroll
             for (int i = 0; i < NOUT; ++i) { lo[i].x = lo[i].y = 0.f; hi[i].x = hi[i].y = 0.f; }
 #pragma unroll
@@ -498,20 +506,31 @@ struct Fwd2d {
                 if (MODE == kFwdRaw) fir_scatter<H1, NGV, HL, TV1>(j, v, a.v1, hi);
             }
             store_rows(lo, dst, a.out_cols, nrow);
-            if (MODE == kFwdRaw) {
-                store_rows(hi, dst + a.zs_band, a.out_cols, nrow);
-#pragma unroll
-                for (int i = 0; i < NOUT; ++i) { lo[i].x = lo[i].y = 0.f; hi[i].x = hi[i].y = 0.f; }
-#pragma unroll
-                for (int j = 0; j < NR; ++j) {
-                    const F2 v = *reinterpret_cast<const F2*>(Bs + (lrow + j) * CA + 2 * cp);
-                    fir_scatter<H0, NGV, HL, TV0>(j, v, a.v0, lo);
-                    fir_scatter<H1, NGV, HL, TV1>(j, v, a.v1, hi);
-                }
-                store_rows(lo, dst + 2 * a.zs_band, a.out_cols, nrow);
-                store_rows(hi, dst + 3 * a.zs_band, a.out_cols, nrow);
-            }
+            if (MODE == kFwdRaw) store_rows(hi, dst + a.zs_band, a.out_cols, nrow);
         }
+        if (DO_B && MODE == kFwdRaw) {
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i) { lo[i].x = lo[i].y = 0.f; hi[i].x = hi[i].y = 0.f; }
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                const F2 v = *reinterpret_cast<const F2*>(Bs + (lrow + j) * CA + 2 * cp);
+                fir_scatter<H0, NGV, HL, TV0>(j, v, a.v0, lo);
+                fir_scatter<H1, NGV, HL, TV1>(j, v, a.v1, hi);
+            }
+            store_rows(lo, dst + 2 * a.zs_band, a.out_cols, nrow);
+            store_rows(hi, dst + 3 * a.zs_band, a.out_cols, nrow);
+        }
+    }
+    static DTCWT_D void phase_cols_real(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        if (kSplitAB) {
+            const int half = tid / (kThreads / 2);                                           // uniform within a warp
+            for (int task = tid - half * (kThreads / 2); task < NTASK; task += kThreads / 2) {
+                if (half == 0) cols_real_task<true, false>(a, sm, bx, by, bz, task);
+                else cols_real_task<false, true>(a, sm, bx, by, bz, task);
+            }
+            return;
+        }
+        for (int task = tid; task < NTASK; task += kThreads) cols_real_task<true, true>(a, sm, bx, by, bz, task);
     }
 
     // kFwdSym: one output row pair of BOTH symmetric filters from the register window w (centre row c): the sums
@@ -616,7 +635,7 @@ struct Fwd2d {
             phase_cols_hh(a, sm, bx, by, bz, tid);
             return;
         }
-        if (MODE == kFwdSym) {
+        if (MODE == kFwdSym || MODE == kFwdSymP) {
             phase_cols_sym(a, sm, bx, by, bz, tid);
             return;
         }
@@ -624,15 +643,34 @@ struct Fwd2d {
             phase_cols_real(a, sm, bx, by, bz, tid);
             return;
         }
+        if (kSplitAB) {
+            const int half = tid / (kThreads / 2);                                           // uniform within a warp
+            for (int task = tid - half * (kThreads / 2); task < NTASK; task += kThreads / 2) {
+                if (half == 0) cols_q2c_task<true, false>(a, sm, bx, by, bz, task);
+                else cols_q2c_task<false, true>(a, sm, bx, by, bz, task);
+            }
+            return;
+        }
+        for (int task = tid; task < NTASK; task += kThreads) cols_q2c_task<true, true>(a, sm, bx, by, bz, task);
+    }
+
+    // one column task of the 2-D mode: DO_A = LoLo + bands 0, 5 from A, DO_B = bands 2, 3 and 1, 4 from B
+    template <bool DO_A, bool DO_B>
+    static DTCWT_D void cols_q2c_task(const Args& a, float* sm, int bx, int by, int bz, int task) {
         const float* As = sm + RX * CX;
         const float* Bs = As + RX * CA;
         constexpr int NCP = P * GW / 2;                           // column pairs of the tile (CA may be padded)
-        for (int task = tid; task < NCP * (GH / NGV); task += kThreads) {
-            const int strip = task / NCP, cp = task - strip * NCP;
-            const int lrow = Q * NGV * strip;
-            const int orow = P * (GH * by + NGV * strip);        // first output row (LoLo coordinates)
-            const int ocol = P * GW * bx + 2 * cp;
-            F2 lo[NOUT], hi[NOUT];
+        const int strip = task / NCP, cp = task - strip * NCP;
+        const int lrow = Q * NGV * strip;
+        const int orow = P * (GH * by + NGV * strip);        // first output row (LoLo coordinates)
+        const int ocol = P * GW * bx + 2 * cp;
+        // output rows / quad rows of this task that lie inside the image (none when its columns lie outside)
+        const int nrow = (ocol < a.out_cols) ? a.out_rows - orow : 0;
+        const int nq = nrow / 2;                              // out_rows is even
+        float* zb = a.yh + 2 * ((int64_t)bz * a.zs_n + (int64_t)(orow / 2) * a.zs_row + ocol / 2);
+        const int64_t bs = 2 * a.zs_band, rs = 2 * a.zs_row;
+        F2 lo[NOUT], hi[NOUT];
+        if (DO_A) {
 #pragma unroll
             for (int i = 0; i < NOUT; ++i) { lo[i].x = lo[i].y = 0.f; hi[i].x = hi[i].y = 0.f; }
 #pragma unroll
@@ -641,18 +679,13 @@ struct Fwd2d {
                 fir_scatter<H0, NGV, HL, TV0>(j, v, a.v0, lo);
                 fir_scatter<H1, NGV, HL, TV1S>(j, v, a.v1s, hi);
             }
-            // output rows / quad rows of this task that lie inside the image (none when its columns lie outside)
-            const int nrow = (ocol < a.out_cols) ? a.out_rows - orow : 0;
-            const int nq = nrow / 2;                              // out_rows is even
-            float* zb = a.yh + 2 * ((int64_t)bz * a.zs_n + (int64_t)(orow / 2) * a.zs_row + ocol / 2);
-            const int64_t bs = 2 * a.zs_band, rs = 2 * a.zs_row;
-            {
-                float* dst = a.lolo + ((int64_t)bz * a.out_rows + orow) * a.out_cols + ocol;
+            float* dst = a.lolo + ((int64_t)bz * a.out_rows + orow) * a.out_cols + ocol;
 #pragma unroll
-                for (int i = 0; i < NOUT; ++i)
-                    if (i < nrow) *reinterpret_cast<F2*>(dst + (int64_t)i * a.out_cols) = lo[i];
-            }
+            for (int i = 0; i < NOUT; ++i)
+                if (i < nrow) *reinterpret_cast<F2*>(dst + (int64_t)i * a.out_cols) = lo[i];
             store_q2c(hi, zb, zb + 5 * bs, rs, nq);              // vertical high x horizontal low -> bands 0, 5
+        }
+        if (DO_B) {
 #pragma unroll
             for (int i = 0; i < NOUT; ++i) { lo[i].x = lo[i].y = 0.f; hi[i].x = hi[i].y = 0.f; }
 #pragma unroll

@@ -84,8 +84,14 @@ fwd2d_kernel(const __grid_constant__ typename K::Args a, const __grid_constant__
         }
     }
     uint32_t parity = 0;
+    // tile coordinates advance incrementally (the stride gridDim.x decomposed once): no division per tile, in particular
+    // none in front of the prefetch of the next tile
+    const int sx = (int)(gridDim.x % tc), sq = (int)(gridDim.x / tc), sy = sq % tr, sz = sq / tr;
+    int bx = (int)(blockIdx.x % tc), by = (int)((blockIdx.x / tc) % tr), bz = (int)(blockIdx.x / (tc * tr));
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int bx = t % tc, by = (t / tc) % tr, bz = t / (tc * tr);
+        int nx = bx + sx, ny = by + sy, nz = bz + sz;
+        if (nx >= tc) { nx -= tc; ++ny; }
+        if (ny >= tr) { ny -= tr; ++nz; }
         if (a.use_tma) {
             mbar_wait(&bar, parity);
             parity ^= 1u;
@@ -101,12 +107,12 @@ fwd2d_kernel(const __grid_constant__ typename K::Args a, const __grid_constant__
         if (a.use_tma) fence_proxy_async_smem();      // this thread's reads / patch writes of the tile precede the next TMA fill
         __syncthreads();
         if (a.use_tma && tid == 0 && t + (int)gridDim.x < ntiles) {
-            const int n = t + gridDim.x, nx = n % tc, ny = (n / tc) % tr, nz = n / (tc * tr);
             mbar_expect_tx(&bar, (uint32_t)(K::RX * K::CX * sizeof(float)));
             tma_load_3d(fused_smem, &tmap, K::col0(nx) - a.pc_lo, K::row0(ny) - a.pr_lo, nz, &bar);
         }
         K::template phase<4>(a, fused_smem, bx, by, bz, tid);
         __syncthreads();
+        bx = nx; by = ny; bz = nz;
     }
 }
 

@@ -233,11 +233,21 @@ class Transform2d(object):
         if t["h0o"].shape[0] % 2 == 0 or t["h1o"].shape[0] % 2 == 0:
             raise ValueError("even-length biorthogonal filters are not supported by the 2-D transform")
         Yh, Ysc = [], []
-        # a LoLo that is only the next level's input (not the pyramid's lowpass, not a requested scale) is scratch
-        LoLo, yh = self._fwd_level1(X, t, ph, pw, internal=(nlevels > 1 and not include_scale))
-        Yh.append(yh)
-        Ysc.append(LoLo)
-        for lev in range(1, nlevels):
+        chained = None
+        if nlevels >= 2 and not include_scale and t["h2o"] is None and t["h2a"] is None:
+            # levels 1 and 2 chunk by chunk with LoLo1 kept in L2 (same kernels, same results; _ops.chain_mode)
+            chained = _ops.fwd2d_level12(X, t["h0o"], t["h1o"], t["h0b"], t["h0a"], t["h1b"], t["h1a"], (ph, pw),
+                                         internal2="lolo2" if nlevels > 2 else None)
+        if chained is not None:
+            LoLo, yh1, yh2 = chained
+            Yh += [yh1, yh2]
+            Ysc += [None, LoLo]
+        else:
+            # a LoLo that is only the next level's input (not the pyramid's lowpass, not a requested scale) is scratch
+            LoLo, yh = self._fwd_level1(X, t, ph, pw, internal=(nlevels > 1 and not include_scale))
+            Yh.append(yh)
+            Ysc.append(LoLo)
+        for lev in range(len(Yh), nlevels):
             LoLo, yh = self._fwd_levelq(LoLo, t, internal=("lolo%d" % (lev + 1)) if (lev < nlevels - 1 and not include_scale) else None)
             Yh.append(yh)
             Ysc.append(LoLo)
@@ -304,18 +314,20 @@ class Transform2d(object):
                 raise ValueError("lowpass and highpass batch sizes differ")
         for lev in range(a, 1, -1):                      # reference :240-273
             want = (2 * Yh[lev - 2].shape[2], 2 * Yh[lev - 2].shape[3])
+            if lev == 2 and t["g2a"] is None and t["g2o"] is None:
+                # levels 2 and 1 chunk by chunk with the level-1 lowpass kept in L2 (_ops.chain_mode)
+                self._check_lowpass(Z, Yh[1])
+                out = _ops.inv2d_level21(Z, Yh[1], Yh[0], t["g0b"], t["g0a"], t["g1b"], t["g1a"], gm[:, 1], t["g0o"], t["g1o"],
+                                         gm[:, 0], self._crops(Z, want))
+                if out is not None:
+                    return out
             Z = self._inv_levelq(Z, Yh[lev - 1], t, gm[:, lev - 1], want)
         if a >= 1:                                        # reference :275-293
             Z = self._inv_level1(Z, Yh[0], t, gm[:, 0])
         return Z
 
     @staticmethod
-    def _check_lowpass(Z, yh):
-        if (Z.shape[1], Z.shape[2]) != (2 * yh.shape[2], 2 * yh.shape[3]):
-            raise ValueError("Sizes of highpasses are not valid for DTWAVEIFM2")
-
-    def _inv_levelq(self, Z, yh, t, g, want):
-        self._check_lowpass(Z, yh)
+    def _crops(Z, want):
         crops = []
         for have, need in zip((2 * Z.shape[1], 2 * Z.shape[2]), want):
             if have == need:
@@ -324,7 +336,16 @@ class Transform2d(object):
                 crops.append(1)      # this level's input had been edge-extended (reference :263-268)
             else:
                 raise ValueError("Sizes of highpasses are not valid for DTWAVEIFM2")
-        cr, cc = crops
+        return tuple(crops)
+
+    @staticmethod
+    def _check_lowpass(Z, yh):
+        if (Z.shape[1], Z.shape[2]) != (2 * yh.shape[2], 2 * yh.shape[3]):
+            raise ValueError("Sizes of highpasses are not valid for DTWAVEIFM2")
+
+    def _inv_levelq(self, Z, yh, t, g, want):
+        self._check_lowpass(Z, yh)
+        cr, cc = self._crops(Z, want)
         if t["g2a"] is None:
             fused = _ops.inv2d_levelq(Z, yh, t["g0b"], t["g0a"], t["g1b"], t["g1a"], g, (cr, cc))
             if fused is not None:

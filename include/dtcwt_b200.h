@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define DTCWT_B200_VERSION 200          /* 0.2.0: + fused 3-D levels */
+#define DTCWT_B200_VERSION 201          /* 0.2.1: + levels 1 and 2 chained through L2 */
 #define DTCWT_B200_MAX_TAPS 32          /* longest filter accepted (qshift_32) */
 
 #define DTCWT_B200_OK 0
@@ -196,6 +196,31 @@ int dtcwt_b200_inv2d_levelq_hh_f32(const float *yh, float *out, int64_t n, int64
 int dtcwt_b200_inv2d_level1_hh_f32(const float *yh, float *out, int64_t n, int64_t rows, int64_t cols, const double *g2o,
                                    int m2, const double *gain, int64_t zs_n, int64_t zs_band, int64_t zs_row,
                                    void *stream);
+
+/* Levels 1 and 2 chained CHUNK images at a time, the level-1 lowpass kept in L2 (same kernels, same results as the
+ * per-level entry points above; what changes is the launch order and the cache policy of one scratch buffer).
+ *   fwd2d_level12  = fwd2d_level1 + fwd2d_levelq per chunk (numpy/transform2d.py:112-160): lolo1 is scratch for
+ *                    chunk images [chunk][rows+pad_r_hi][cols+pad_c_hi]; level 2 pads by one replicated sample per
+ *                    side where that size is not a multiple of 4 (:134-140); lolo2 / yh1 / yh2 are the batch outputs.
+ *   inv2d_level21  = inv2d_levelq + inv2d_level1 per chunk (:240-293): z2 [n][rows2][cols2] enters level 2, z1 is
+ *                    scratch [chunk][2 rows2 - 2 crop_r][2 cols2 - 2 crop_c], out has that size per image.
+ *   persist        0: plain launch order change; 1..100: the scratch is marked L2-persisting on `stream` for the
+ *                    duration of the call (cudaStreamAttributeAccessPolicyWindow, hit ratio persist / 100), so it is
+ *                    written and re-read inside L2 and the 8 B/pixel of its HBM round trip disappear.
+ *   l2_info        {max persisting bytes, max access-policy window bytes, L2 bytes} of the current device. */
+int dtcwt_b200_fwd2d_level12_f32(const float *x, float *lolo1, float *lolo2, float *yh1, float *yh2, int64_t n,
+                                 int64_t rows, int64_t cols, int pad_r_hi, int pad_c_hi, const double *h0o, int m0,
+                                 const double *h1o, int m1, const double *lo_a, const double *lo_b,
+                                 const double *hi_a, const double *hi_b, int m, int64_t zs1_n, int64_t zs1_band,
+                                 int64_t zs1_row, int64_t zs2_n, int64_t zs2_band, int64_t zs2_row, int64_t chunk,
+                                 int persist, void *stream);
+int dtcwt_b200_inv2d_level21_f32(const float *z2, const float *yh2, const float *yh1, float *z1, float *out, int64_t n,
+                                 int64_t rows2, int64_t cols2, int crop_r, int crop_c, const double *lo_a,
+                                 const double *lo_b, const double *hi_a, const double *hi_b, int m,
+                                 const double *gain2, const double *g0o, int m0, const double *g1o, int m1,
+                                 const double *gain1, int64_t zs2_n, int64_t zs2_band, int64_t zs2_row, int64_t zs1_n,
+                                 int64_t zs1_band, int64_t zs1_row, int64_t chunk, int persist, void *stream);
+int dtcwt_b200_l2_info(int64_t *out3);
 
 /* ---- fused per-level 3-D transform (float32) -----------------------------------
  * A level of Transform3d is two launches: the two in-slice axes of every slice in one

@@ -162,6 +162,7 @@ static int launch_fwds1(typename K::Args& a, void* /*stream*/) {
 #include "../../dtcwt_b200/csrc/abi_fused2d.inl"
 #include "../../dtcwt_b200/csrc/abi_axis.inl"
 #include "../../dtcwt_b200/csrc/abi_fused3d.inl"
+#include "../../dtcwt_b200/csrc/abi_chain.inl"
 
 extern "C" {
 

@@ -23,7 +23,7 @@ class Launches(object):
     def __init__(self):
         self.names = []
 
-    def __call__(self, symbol, thunk):
+    def __call__(self, symbol, thunk, launches=1):
         self.names.append(symbol)
         thunk()
 
@@ -299,3 +299,33 @@ def test_symmetric_sum_column_pass_matches(backend, monkeypatch):
         for i in range(shape[0]):
             po = to.forward(X[i], 1)
             assert rel_err(p1.lowpass[i], po.lowpass) < REL_TOL and rel_err(p1.highpasses[0][i], po.highpasses[0]) < REL_TOL
+
+
+@pytest.mark.parametrize("mode", ["-1", "100"])
+@pytest.mark.parametrize("shape,nlevels", [((3, 96, 128), 3), ((5, 130, 150), 2), ((2, 65, 131), 4)])
+def test_chained_levels_match_per_level_launches(backend, monkeypatch, mode, shape, nlevels):
+    """Levels 1 and 2 chained chunk by chunk through the L2-resident scratch (dtcwt_b200_fwd2d_level12_f32 /
+    inv2d_level21_f32) give bit-identical results to one launch per level: same kernels, only the order changes.
+    Covers a chunk that does not divide the batch, the level-2 edge padding (130 % 4 != 0) and odd sizes."""
+    rng = np.random.RandomState(5)
+    X = rng.rand(*shape).astype(np.float32)
+    gain = rng.rand(6, nlevels)
+    xf = dtcwt_b200.Transform2d("near_sym_b", "qshift_b")
+    monkeypatch.setenv("DTCWT_B200_CHAIN", "0")
+    p0 = xf.forward_channels(X, "nhw", nlevels=nlevels)
+    Z0 = npy(xf.inverse_channels(p0, "nhw", gain_mask=gain))
+    ref = [npy(p0.lowpass_t)] + [npy(h) for h in p0.highpasses_t]
+    monkeypatch.setenv("DTCWT_B200_CHAIN", mode)
+    monkeypatch.setenv("DTCWT_B200_CHAIN_MIN_PIX", "1")
+    per = 4 * (shape[1] + shape[1] % 2) * (shape[2] + shape[2] % 2)
+    monkeypatch.setenv("DTCWT_B200_CHAIN_MB", "1")               # 1 MiB budget: 2 .. 21 images per chunk
+    assert _ops.chain_chunk(shape[0], shape[1] + shape[1] % 2, shape[2] + shape[2] % 2) == min(shape[0], (1 << 20) // per)
+    with Launches() as L:
+        p1 = xf.forward_channels(X, "nhw", nlevels=nlevels)
+        Z1 = npy(xf.inverse_channels(p1, "nhw", gain_mask=gain))
+    assert "dtcwt_b200_fwd2d_level12_f32" in L.names and "dtcwt_b200_inv2d_level21_f32" in L.names, L.names
+    assert "dtcwt_b200_fwd2d_level1_f32" not in L.names and "dtcwt_b200_inv2d_level1_f32" not in L.names
+    got = [npy(p1.lowpass_t)] + [npy(h) for h in p1.highpasses_t]
+    for a, b in zip(got, ref):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    assert np.array_equal(Z0, Z1)
