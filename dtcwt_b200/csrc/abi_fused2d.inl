@@ -123,6 +123,9 @@ template <int M> struct InvLqHH { typedef Inv2d<SpecInt<M, true>, SpecInt<M, fal
 // levels >= 2: q-shift pairs; every shipped family has a positive lowpass and a negative highpass tap correlation
 template <int M> struct FwdLq { typedef Fwd2d<SpecDec<M, true>, SpecDec<M, false>, 32, 16, 4> type; };
 template <int M> struct InvLq { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4> type; };
+// the same with the row pass on interleaved row pairs (all FFMA2); qshift_b: taps as immediates
+template <int M> struct InvLqP { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4, false, false, RtPhase, RtPhase, true> type; };
+typedef Inv2d<SpecInt<14, true>, SpecInt<14, false>, 4, 1, 4, false, false, BakedPhaseQ<QshiftB_g0>, BakedPhaseQ<QshiftB_g1>, true> InvLqP_qb;
 // levels >= 2 inverse: streaming kernels for the 10- and 14-tap families (ring of 4 * (m/2 + 1) output rows); opt-in
 typedef InvSq<14, 32, 2, BakedPhase2<QshiftB_g0>, BakedPhase2<QshiftB_g1> > InvSq_qb;     // qshift_b, taps as immediates
 typedef InvSq<14, 32, 2> InvSq_14;
@@ -369,6 +372,18 @@ int dtcwt_b200_inv2d_levelq_f32(const float* z, const float* yh, float* out, int
         }
         s.periods = choose_periods(2 * s.rows, InvSq_14::RING, (int64_t)InvSq_14::tiles_c(s) * s.n);
         return launch_invs1<InvSq_14>(s, stream);
+    }
+    // DTCWT_B200_INVQ_VARIANT: 0 (default) = single-row row pass (unpacked FFMA), 1 = row pairs (all FFMA2) with runtime taps,
+    // 2 = row pairs with baked immediates for qshift_b.  Measured 0.736 / 0.766 / 0.754 ms per 16 x 4096^2 step
+    // (profiles/r3_01): a third fewer instructions did not make the kernel faster, so the variants stay opt-in.
+    const int v = env_int("DTCWT_B200_INVQ_VARIANT", 0);
+    if (m == 14 && v == 2 && BakedPhaseQ<QshiftB_g0>::same(a.g0) && BakedPhaseQ<QshiftB_g1>::same(a.g1))
+        return launch_inv2d<InvLqP_qb>(a, stream);
+    if (v >= 1) {
+        if (m == 10) return launch_inv2d<InvLqP<10>::type>(a, stream);
+        if (m == 14) return launch_inv2d<InvLqP<14>::type>(a, stream);
+        if (m == 16) return launch_inv2d<InvLqP<16>::type>(a, stream);
+        return launch_inv2d<InvLqP<18>::type>(a, stream);
     }
     if (m == 10) return launch_inv2d<InvLq<10>::type>(a, stream);
     if (m == 14) return launch_inv2d<InvLq<14>::type>(a, stream);

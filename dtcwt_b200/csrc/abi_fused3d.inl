@@ -16,6 +16,9 @@ static const int kFused3dMinSide = 32, kFused3dMinSideInv = 16;
 // slice kernels of the 3-D levels
 template <int M> struct FwdLqRaw { typedef Fwd2d<SpecDec<M, true>, SpecDec<M, false>, 32, 16, 4, RtPhase, RtPhase, RtPhase, kFwdRaw> type; };
 template <int M> struct InvLqRaw { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4, true> type; };
+// row pass on interleaved row pairs (fused2d.cuh: ROWPAIR); qshift_b with its taps as immediates
+template <int M> struct InvLqRawP { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4, true, false, RtPhase, RtPhase, true> type; };
+typedef Inv2d<SpecInt<14, true>, SpecInt<14, false>, 4, 1, 4, true, false, BakedPhaseQ<QshiftB_g0>, BakedPhaseQ<QshiftB_g1>, true> InvLqRawP_qb;
 typedef Fwd2d<SpecCol<19>, SpecCol<19>, 64, 64, 8, RtPhase, RtPhase, RtPhase, kFwdRaw> FwdT1Raw;
 typedef Inv2d<SpecCol<19>, SpecCol<19>, 8, 1, 4, true> InvT1Raw;
 typedef Fwd2d<SpecCol<13, kMask13>, SpecCol<13>, 64, 64, 8, RtPhase, RtPhase, RtPhase, kFwdLow> FwdLow13m;   // near_sym_b h0o
@@ -249,6 +252,15 @@ int dtcwt_b200_inv3d_levelq_f32(const float* yl, const float* yh, float* out, fl
     for (int b = 0; b < 6; ++b) a.gain[b] = 1.f;
     taps_int(a.g0, lo_a, lo_b, m, true);
     taps_int(a.g1, hi_a, hi_b, m, false);
+    const int v = env_int("DTCWT_B200_INVQ_VARIANT", 0);       // see dtcwt_b200_inv2d_levelq_f32
+    if (m == 14 && v == 2 && BakedPhaseQ<QshiftB_g0>::same(a.g0) && BakedPhaseQ<QshiftB_g1>::same(a.g1))
+        return launch_inv2d<InvLqRawP_qb>(a, stream);
+    if (v >= 1) {
+        if (m == 10) return launch_inv2d<InvLqRawP<10>::type>(a, stream);
+        if (m == 14) return launch_inv2d<InvLqRawP<14>::type>(a, stream);
+        if (m == 16) return launch_inv2d<InvLqRawP<16>::type>(a, stream);
+        return launch_inv2d<InvLqRawP<18>::type>(a, stream);
+    }
     if (m == 10) return launch_inv2d<InvLqRaw<10>::type>(a, stream);
     if (m == 14) return launch_inv2d<InvLqRaw<14>::type>(a, stream);
     if (m == 16) return launch_inv2d<InvLqRaw<16>::type>(a, stream);

@@ -170,6 +170,23 @@ DTCWT_D void fir_gather(const float (&w)[WN], const PhaseTaps& t, float (&acc)[F
     }
 }
 
+// The same on a window of ROW PAIRS: w[j] holds column j of two adjacent rows, one FFMA2 with a scalar tap advances the
+// output of both rows (TS: tap source, see below -- immediates for a baked table)
+template <class F, int NG, int HALO, int WN, class TS>
+DTCWT_D void fir_gather2(const F2 (&w)[WN], const PhaseTaps& t, F2 (&acc)[F::P * NG]) {
+#pragma unroll
+    for (int ii = 0; ii < NG; ++ii) {
+#pragma unroll
+        for (int ph = 0; ph < F::P; ++ph) {
+            F2 s = acc[F::P * ii + ph];
+#pragma unroll
+            for (int k = 0; k < F::K; ++k)
+                if (F::on(ph, k)) s = fma2(TS::get(t, ph, k), w[F::Q * ii + F::b(ph) + F::S * k + HALO], s);
+            acc[F::P * ii + ph] = s;
+        }
+    }
+}
+
 // Tap source of a scatter: the kernel arguments, or a table baked into the instance (FFMA2 immediates).
 struct RtPhase {
     static DTCWT_D float get(const PhaseTaps& t, int ph, int k) { return t.t[ph][k]; }
@@ -177,6 +194,16 @@ struct RtPhase {
 template <class B>
 struct BakedPhase {
     static DTCWT_D float get(const PhaseTaps&, int, int k) { return B::get(k); }
+};
+template <class B>
+struct BakedPhaseQ {                       // phase tables t[ph][k] (colifilt), baked
+    static DTCWT_D float get(const PhaseTaps&, int ph, int k) { return B::get(ph, k); }
+    static bool same(const PhaseTaps& t) {
+        for (int ph = 0; ph < 4; ++ph)
+            for (int k = 0; k < B::K; ++k)
+                if (!(t.t[ph][k] == B::get(ph, k))) return false;
+        return true;
+    }
 };
 
 // Input row j (relative to the window start, HALO rows before the first group) contributes to
@@ -295,6 +322,11 @@ struct Fwd2d {
     }
     static DTCWT_HD bool touches_edge(int L0, int extent, int pad_lo, int len) {
         return (L0 - pad_lo < 0) || (L0 + extent - pad_lo > len);
+    }
+
+    // the tile reaches outside the stored image (uniform over the CTA): only then do the patch phases have work
+    static DTCWT_HD bool tile_on_edge(const Args& a, int bx, int by) {
+        return touches_edge(row0(by), RX, a.pr_lo, a.rows) || touches_edge(col0(bx), CX, a.pc_lo, a.cols);
     }
 
     // phase 1 / 2: symmetric extension (utils.py:136-153) of tiles on the image border, inside smem
@@ -736,10 +768,16 @@ struct Inv2dArgs {
 // s0..s3 of Fwd2d's kFwdRaw mode, image s at z + s * zs_band (floats), instead of lowpass + complex sub-bands.
 // HH (`_bp` families, transform2d.py:254-262): the second launch of a level -- the lowpass counts as zero and the result is
 // ADDED to `out`; with the gains of the other four sub-bands zero and g2 in the G1 slot that is H:g2(V:g2(c2q(bands 1, 4))).
-template <class G0, class G1, int NGV_, int NSTRIP_, int NWIDE_, bool RAW_ = false, bool HH_ = false>
+// ROWPAIR: y1 / y2 are kept in shared memory as interleaved ROW PAIRS ((row 2i, row 2i+1) of a column adjacent), so the row
+// pass runs on pairs of rows with packed FFMA2 and scalar taps -- immediates when the taps are baked (TS0 / TS1), which
+// also takes the constant loads (LDCU) out of the column pass.  The kernel is issue-bound (profiles/r2_04: 74 % issue
+// active, a third of its instructions unpacked FFMA of the row pass), so halving the row pass's FMA instructions pays.
+template <class G0, class G1, int NGV_, int NSTRIP_, int NWIDE_, bool RAW_ = false, bool HH_ = false, class TS0 = RtPhase,
+          class TS1 = RtPhase, bool ROWPAIR_ = false>
 struct Inv2d {
     typedef Inv2dArgs Args;
-    static constexpr bool RAW = RAW_, HH = HH_;
+    static constexpr bool RAW = RAW_, HH = HH_, ROWPAIR = ROWPAIR_;
+    static_assert(!(ROWPAIR_ && HH_), "the accumulate-into-out variant keeps the single-row row pass");
     static constexpr int P = G0::P, Q = G0::Q;
     static constexpr int NGV = NGV_, NSTRIP = NSTRIP_, NWIDE = NWIDE_;
     static constexpr int NGH = 4 / Q;
@@ -757,7 +795,10 @@ struct Inv2d {
     static constexpr int NOUT = P * NGV;
     static constexpr int WN = round_up(HLC + 4 + HR, 4);                 // register window of a row task
     static constexpr int NSEG = TWI / 4;
-    static constexpr int kSmemFloats = 2 * RY * CY;
+    // ROWPAIR: pitch of a pair row (2 CY floats) padded by 4, so that adjacent pair rows sit one 16-byte bank group apart
+    static constexpr int PYP = 2 * CY + 4;
+    static constexpr int kImgFloats = ROWPAIR_ ? (RY / 2) * PYP : RY * CY;      // one of y1 / y2
+    static constexpr int kSmemFloats = 2 * kImgFloats;
     static constexpr int kPhases = 2;
     static constexpr int kMinBlocks = 3;                                 // register budget: 3 CTAs (24 warps) per SM
     static_assert(P == G1::P && Q == G1::Q, "filter pair must share its rate");
@@ -865,11 +906,22 @@ struct Inv2d {
                 flip_quad(false, fc, at, ab);
                 flip_quad(false, fc, bt, bb);
             }
-            fir_scatter<G0, NGV, HLR>(2 * jq, at, a.g0, acc);
-            fir_scatter<G1, NGV, HLR>(2 * jq, bt, a.g1, acc);
-            fir_scatter<G0, NGV, HLR>(2 * jq + 1, ab, a.g0, acc);
-            fir_scatter<G1, NGV, HLR>(2 * jq + 1, bb, a.g1, acc);
+            fir_scatter<G0, NGV, HLR, TS0>(2 * jq, at, a.g0, acc);
+            fir_scatter<G1, NGV, HLR, TS1>(2 * jq, bt, a.g1, acc);
+            fir_scatter<G0, NGV, HLR, TS0>(2 * jq + 1, ab, a.g0, acc);
+            fir_scatter<G1, NGV, HLR, TS1>(2 * jq + 1, bb, a.g1, acc);
             cur = nxt;
+        }
+        if (ROWPAIR) {
+            // pair row p = rows (2p, 2p+1): element (p, col, parity) at p * 2CY + 2 col + parity
+            float* y = sm + ROLE * kImgFloats + (NOUT / 2 * strip) * PYP + 4 * qc;
+#pragma unroll
+            for (int i = 0; i < NOUT; i += 2) {
+                F4 v;
+                v.x = acc[i].x; v.y = acc[i + 1].x; v.z = acc[i].y; v.w = acc[i + 1].y;
+                *reinterpret_cast<F4*>(y + (i / 2) * PYP) = v;
+            }
+            return;
         }
         float* y = sm + ROLE * RY * CY + (NOUT * strip) * CY + 2 * qc;
 #pragma unroll
@@ -891,8 +943,84 @@ struct Inv2d {
         }
     }
 
+    // one row of a row-pair task: P * NGH outputs from c0 on
+    static DTCWT_D void store_pair_row(const Args& a, float* img, int r, int c0, const float (&o)[P * NGH]) {
+        if (r < 0 || r >= a.out_rows) return;
+        float* d = img + (int64_t)r * a.out_cols + c0;
+        if (a.out_vec4 && c0 + P * NGH <= a.out_cols) {                // 16-byte aligned rows, no crop
+#pragma unroll
+            for (int c = 0; c < (P * NGH) / 4; ++c) {
+                F4 v;
+                v.x = o[4 * c]; v.y = o[4 * c + 1]; v.z = o[4 * c + 2]; v.w = o[4 * c + 3];
+                reinterpret_cast<F4*>(d)[c] = v;
+            }
+        } else if (a.crop_c == 0) {                                    // rows are 8-byte aligned
+#pragma unroll
+            for (int i = 0; i < P * NGH; i += 2)
+                if (c0 + i < a.out_cols) {
+                    F2 v;
+                    v.x = o[i]; v.y = o[i + 1];
+                    *reinterpret_cast<F2*>(d + i) = v;
+                }
+        } else {
+#pragma unroll
+            for (int i = 0; i < P * NGH; ++i)
+                if (c0 + i >= 0 && c0 + i < a.out_cols) d[i] = o[i];
+        }
+    }
+
+    // phase 1, ROWPAIR: one task = one PAIR of output rows x 4 input columns, every multiply-add a packed FFMA2
+    static DTCWT_D void phase_rows_pair(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        const float* y1 = sm;
+        const float* y2 = sm + kImgFloats;
+        float* img = a.out + (int64_t)bz * a.out_rows * a.out_cols;
+        static_assert(((RY / 2) % 2) == 0, "pair rows are handed out two at a time");
+        // adjacent lanes take adjacent pair rows of the same segment (one bank group apart: PYP), lane pairs walk along the
+        // segments (two bank groups apart): a quarter-warp of 16-byte loads touches eight different bank groups
+        for (int task = tid; task < (RY / 2) * NSEG; task += kThreads) {
+            const int half = task >> 1;
+            const int lp = 2 * (half / NSEG) + (task & 1), seg = half % NSEG;
+            const int r = P * GH * by + 2 * lp - a.crop_r;             // first row of the pair
+            if (r + 1 < 0 || r >= a.out_rows) continue;
+            F2 acc[P * NGH];
+#pragma unroll
+            for (int i = 0; i < P * NGH; ++i) acc[i] = zero2();
+            F2 w[WN];
+            {
+                const F4* src = reinterpret_cast<const F4*>(y1 + lp * PYP + 2 * (seg * 4));
+#pragma unroll
+                for (int c = 0; c < WN / 2; ++c) {
+                    const F4 v = src[c];
+                    w[2 * c].x = v.x; w[2 * c].y = v.y; w[2 * c + 1].x = v.z; w[2 * c + 1].y = v.w;
+                }
+                fir_gather2<G0, NGH, HLC, WN, TS0>(w, a.g0, acc);
+            }
+            {
+                const F4* src = reinterpret_cast<const F4*>(y2 + lp * PYP + 2 * (seg * 4));
+#pragma unroll
+                for (int c = 0; c < WN / 2; ++c) {
+                    const F4 v = src[c];
+                    w[2 * c].x = v.x; w[2 * c].y = v.y; w[2 * c + 1].x = v.z; w[2 * c + 1].y = v.w;
+                }
+                fir_gather2<G1, NGH, HLC, WN, TS1>(w, a.g1, acc);
+            }
+            const int c0 = (P / Q) * (TWI * bx + 4 * seg) - a.crop_c;     // first output column of the task
+            float o[P * NGH];
+#pragma unroll
+            for (int i = 0; i < P * NGH; ++i) o[i] = acc[i].x;
+            store_pair_row(a, img, r, c0, o);
+#pragma unroll
+            for (int i = 0; i < P * NGH; ++i) o[i] = acc[i].y;
+            store_pair_row(a, img, r + 1, c0, o);
+        }
+    }
+
     // phase 1: row pass out = H:g0(y1) + H:g1(y2); one task = one output row x 4 input columns
     static DTCWT_D void phase_rows(const Args& a, float* sm, int bx, int by, int bz, int tid) {
+        if (ROWPAIR) {
+            phase_rows_pair(a, sm, bx, by, bz, tid);
+            return;
+        }
         const float* y1 = sm;
         const float* y2 = sm + RY * CY;
         float* img = a.out + (int64_t)bz * a.out_rows * a.out_cols;

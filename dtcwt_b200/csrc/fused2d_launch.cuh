@@ -55,15 +55,18 @@ fwd2d_kernel(const __grid_constant__ typename K::Args a, const __grid_constant__
                 tma_load_3d(fused_smem, &tmap, K::col0(bx) - a.pc_lo, K::row0(by) - a.pr_lo, bz, &bar);
             }
             __syncthreads();
-            mbar_wait(&bar, 0);
+            mbar_wait(&bar, 0);            // every thread observes the completion itself: the tile is visible to it
         } else {
             K::template phase<0>(a, fused_smem, bx, by, bz, tid);
+            __syncthreads();
         }
-        __syncthreads();
-        K::template phase<1>(a, fused_smem, bx, by, bz, tid);
-        __syncthreads();
-        K::template phase<2>(a, fused_smem, bx, by, bz, tid);
-        __syncthreads();
+        // interior tiles (the CTA-uniform common case) have nothing to patch and skip those two barriers
+        if (K::tile_on_edge(a, bx, by)) {
+            K::template phase<1>(a, fused_smem, bx, by, bz, tid);
+            __syncthreads();
+            K::template phase<2>(a, fused_smem, bx, by, bz, tid);
+            __syncthreads();
+        }
         K::template phase<3>(a, fused_smem, bx, by, bz, tid);
         __syncthreads();
         K::template phase<4>(a, fused_smem, bx, by, bz, tid);
@@ -97,12 +100,14 @@ fwd2d_kernel(const __grid_constant__ typename K::Args a, const __grid_constant__
             parity ^= 1u;
         } else {
             K::template phase<0>(a, fused_smem, bx, by, bz, tid);
+            __syncthreads();
         }
-        __syncthreads();
-        K::template phase<1>(a, fused_smem, bx, by, bz, tid);
-        __syncthreads();
-        K::template phase<2>(a, fused_smem, bx, by, bz, tid);
-        __syncthreads();
+        if (K::tile_on_edge(a, bx, by)) {
+            K::template phase<1>(a, fused_smem, bx, by, bz, tid);
+            __syncthreads();
+            K::template phase<2>(a, fused_smem, bx, by, bz, tid);
+            __syncthreads();
+        }
         K::template phase<3>(a, fused_smem, bx, by, bz, tid);
         if (a.use_tma) fence_proxy_async_smem();      // this thread's reads / patch writes of the tile precede the next TMA fill
         __syncthreads();

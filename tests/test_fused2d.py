@@ -329,3 +329,37 @@ def test_chained_levels_match_per_level_launches(backend, monkeypatch, mode, sha
     for a, b in zip(got, ref):
         assert a.shape == b.shape and np.array_equal(a, b)
     assert np.array_equal(Z0, Z1)
+
+
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_row_pair_inverse_qshift_matches(backend, monkeypatch, variant):
+    """The q-shift inverse tile kernel with its row pass on interleaved row pairs (opt-in: DTCWT_B200_INVQ_VARIANT=1 runtime
+    taps, 2 baked qshift_b immediates; 2-D and the 3-D slice mode) agrees with the default single-row row pass to rounding --
+    cropped levels (130 % 4 != 0), image borders and gains included -- and with the oracle at the stated tolerance."""
+    rs = np.random.RandomState(47)
+    gain = rs.rand(6, 2)
+    for shape, names in (((2, 96, 200), ("near_sym_b", "qshift_b")), ((1, 130, 150), ("near_sym_b", "qshift_b")),
+                         ((1, 72, 264), ("near_sym_a", "qshift_a"))):
+        X = rs.rand(*shape).astype(np.float32)
+        xf = dtcwt_b200.Transform2d(*names)
+        p = xf.forward_channels(X, "nhw", 2)
+        monkeypatch.setenv("DTCWT_B200_INVQ_VARIANT", "0")
+        Z0 = npy(xf.inverse_channels(p, "nhw", gain))
+        monkeypatch.setenv("DTCWT_B200_INVQ_VARIANT", variant)
+        with Launches() as L:
+            Z1 = npy(xf.inverse_channels(p, "nhw", gain))
+        monkeypatch.delenv("DTCWT_B200_INVQ_VARIANT")
+        assert L.only_fused(), L.names
+        assert np.abs(Z0 - Z1).max() < 2e-6 * np.abs(Z0).max()
+        to = O.Transform2d(coeffs.biort(names[0]), coeffs.qshift(names[1]))
+        for i in range(shape[0]):
+            assert rel_err(Z1[i], to.inverse(to.forward(X[i], 2), gain)) < REL_TOL
+    V = rs.rand(1, 32, 40, 48).astype(np.float32)
+    x3 = dtcwt_b200.Transform3d("near_sym_b", "qshift_b")
+    p3 = x3.forward(V[0], 2)
+    monkeypatch.setenv("DTCWT_B200_INVQ_VARIANT", "0")
+    W0 = npy(x3.inverse(p3))
+    monkeypatch.setenv("DTCWT_B200_INVQ_VARIANT", variant)
+    W1 = npy(x3.inverse(p3))
+    monkeypatch.delenv("DTCWT_B200_INVQ_VARIANT")
+    assert np.abs(W0 - W1).max() < 2e-6 * np.abs(W0).max() and np.abs(W1 - V[0]).max() < 1e-5
