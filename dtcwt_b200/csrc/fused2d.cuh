@@ -317,7 +317,10 @@ struct Fwd2d {
     static DTCWT_HD int mirror_src(int L, int Ltot, int pad_lo, int len, int L0, int extent) {
         const int s = L - pad_lo;
         if (s >= 0 && s < len) return -2;                                  // directly loaded
-        const int l = unpad(reflect_any(L, Ltot), pad_lo, len) + pad_lo - L0;
+        // one fold covers every halo that is shorter than the image; reflect_any's modulo only for tinier images
+        int r = L < 0 ? -1 - L : (L >= Ltot ? 2 * Ltot - 1 - L : L);
+        if ((unsigned)r >= (unsigned)Ltot) r = reflect_any(L, Ltot);
+        const int l = unpad(r, pad_lo, len) + pad_lo - L0;
         return (l >= 0 && l < extent) ? l : -1;
     }
     static DTCWT_HD bool touches_edge(int L0, int extent, int pad_lo, int len) {
@@ -359,7 +362,20 @@ struct Fwd2d {
         outside_range(L0, CX, a.pc_lo, a.cols, n_lo, hi0);
         const int n_out = n_lo + (CX - hi0);
         if (n_out == 0) return;
-        for (int e = tid; e < RX * n_out; e += kThreads) {
+        if (n_out <= 32) {
+            // the usual case (the halo of one or both sides): rows x outside columns with the columns padded to a power of
+            // two, so that no division by a run-time count is needed
+            const int sh = n_out <= 8 ? 3 : (n_out <= 16 ? 4 : 5);
+            for (int e = tid; e < (RX << sh); e += kThreads) {
+                const int lr = e >> sh, k = e & ((1 << sh) - 1);
+                if (k >= n_out) continue;
+                const int lc = k < n_lo ? k : hi0 + (k - n_lo);
+                const int src = mirror_src(L0 + lc, a.Lc, a.pc_lo, a.cols, L0, CX);
+                if (src >= 0) sm[lr * CX + lc] = sm[lr * CX + src];
+            }
+            return;
+        }
+        for (int e = tid; e < RX * n_out; e += kThreads) {         // images narrower than a tile
             const int lr = e / n_out, k = e - lr * n_out;
             const int lc = k < n_lo ? k : hi0 + (k - n_lo);
             const int src = mirror_src(L0 + lc, a.Lc, a.pc_lo, a.cols, L0, CX);
