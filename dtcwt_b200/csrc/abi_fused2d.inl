@@ -109,6 +109,12 @@ typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps
 typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 2, 2> InvL1_nsbC;   // arithmetic only
 #endif
 typedef InvS1<19, 19, 0x7ffffu, 0x7ffffu, 24, 3> InvL1_19_19;       // any odd pair up to 19 taps (zero-padded)
+// the same with the prefetched quad rows staged in shared memory by per-thread cp.async (last argument: stages)
+typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 2, 0, false, 6> InvL1_nsbA;
+typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 2, 0, false, 4> InvL1_nsbA4;
+typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 3, 0, false, 3> InvL1_nsbA3;   // 3 CTAs per SM
+typedef InvS1<19, 19, 0x7ffffu, 0x7ffffu, 24, 3, ArgTaps, ArgTaps, 2, 0, false, 6> InvL1_19_19A;
+typedef InvS1<7, 5, 0x7fu, 0x1fu, 8, 2, ArgTaps, ArgTaps, 2, 0, false, 4> InvL1_7_5A;
 // the same with the inputs staged by bulk copies (ring, stages); opt-in (DTCWT_B200_INV_STAGED=1), see dtcwt_b200_inv2d_level1_f32
 typedef InvS1T<19, 13, kMask19, kMask13, 24, 6, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1> > InvT1_nsb;
 typedef InvS1T<19, 13, kMask19, kMask13, 24, 4, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1> > InvT1_nsb4;   // experiment: DTCWT_B200_INV_NSTAGE=4
@@ -459,9 +465,21 @@ int dtcwt_b200_inv2d_level1_f32(const float* z, const float* yh, float* out, int
         a.periods = choose_periods(a.rows, InvT1_19_19::RING, (int64_t)InvT1_19_19::tiles_c(a) * a.n);
         return launch_invs1t<InvT1_19_19>(a, stream);
     }
+    // DTCWT_B200_INV_ASYNC: stages of the per-thread cp.async prefetch (0: register stages, the round-2 kernel)
+    const int nasync = env_int("DTCWT_B200_INV_ASYNC", 6);
+    if (small && nasync > 0) {
+        a.periods = choose_periods(a.rows, InvL1_7_5A::RING, (int64_t)InvL1_7_5A::tiles_c(a) * a.n);
+        return launch_invs1<InvL1_7_5A>(a, stream);
+    }
     if (small) {
         a.periods = choose_periods(a.rows, InvL1_7_5::RING, (int64_t)InvL1_7_5::tiles_c(a) * a.n);
         return launch_invs1<InvL1_7_5>(a, stream);
+    }
+    if (nasync > 0 && K1 == 13 && BakedTaps<NearSymB_g0>::same(a.g0) && BakedTaps<NearSymB_g1>::same(a.g1)) {
+        a.periods = choose_periods(a.rows, InvL1_nsbA::RING, (int64_t)InvL1_nsbA::tiles_c(a) * a.n);
+        if (nasync == 4) return launch_invs1<InvL1_nsbA4>(a, stream);
+        if (nasync == 3) return launch_invs1<InvL1_nsbA3>(a, stream);
+        return launch_invs1<InvL1_nsbA>(a, stream);
     }
     if (K1 == 13 && BakedTaps<NearSymB_g0>::same(a.g0) && BakedTaps<NearSymB_g1>::same(a.g1)) {
 #ifdef DTCWT_DIAGNOSIS
@@ -481,6 +499,10 @@ int dtcwt_b200_inv2d_level1_f32(const float* z, const float* yh, float* out, int
     if (K1 == 13) {                  // the general instance takes two 19-slot filters
         taps_col_s(a.g1, g1o, m1, 19, 1.0);
         pair_tab(a.p1, a.g1, 19);
+    }
+    if (nasync > 0) {
+        a.periods = choose_periods(a.rows, InvL1_19_19A::RING, (int64_t)InvL1_19_19A::tiles_c(a) * a.n);
+        return launch_invs1<InvL1_19_19A>(a, stream);
     }
     a.periods = choose_periods(a.rows, InvL1_19_19::RING, (int64_t)InvL1_19_19::tiles_c(a) * a.n);
     return launch_invs1<InvL1_19_19>(a, stream);

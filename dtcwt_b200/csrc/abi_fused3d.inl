@@ -203,6 +203,13 @@ int dtcwt_b200_fwd3d_levelq_f32(const float* x, float* lll, float* yh, float* sc
     z.sub_stride = sub; z.vol_stride = d0 * (L1 / 2) * (L2 / 2);
     taps_dec(z.lo, lo_a, lo_b, m, true, 0.5);
     taps_dec(z.hi, hi_a, hi_b, m, false, 0.5);
+    // DTCWT_B200_Z3_SPLIT=0: both rows of a 2 x 2 patch in one thread, NG = 2 (the round-2 kernels)
+    if (env_int("DTCWT_B200_Z3_SPLIT", 0)) {
+        if (m == 10) return launch_z3<Z3FwdS<SpecDec<10, true>, SpecDec<10, false>, 4> >(z, stream);
+        if (m == 14) return launch_z3<Z3FwdS<SpecDec<14, true>, SpecDec<14, false>, 4> >(z, stream);
+        if (m == 16) return launch_z3<Z3FwdS<SpecDec<16, true>, SpecDec<16, false>, 4> >(z, stream);
+        return launch_z3<Z3FwdS<SpecDec<18, true>, SpecDec<18, false>, 4> >(z, stream);
+    }
     if (m == 10) return launch_z3<Z3FwdQ<10>::type>(z, stream);
     if (m == 14 && env_int("DTCWT_B200_Z3_NG", 2) == 4) return launch_z3<Z3Fwd<SpecDec<14, true>, SpecDec<14, false>, 4> >(z, stream);
     if (m == 14) return launch_z3<Z3FwdQ<14>::type>(z, stream);
@@ -236,7 +243,16 @@ int dtcwt_b200_inv3d_levelq_f32(const float* yl, const float* yh, float* out, fl
     z.sub_stride = sub; z.vol_stride = od0 * a1 * a2;
     taps_int(z.lo, lo_a, lo_b, m, true, 0.5);
     taps_int(z.hi, hi_a, hi_b, m, false, 0.5);
-    if (m == 10) rc = launch_z3<Z3InvQ<10>::type>(z, stream);
+    const int zdepth = env_int("DTCWT_B200_Z3_ASYNC", 3);      // octets staged ahead by cp.async (0: plain loads, the round-2 kernel)
+    if (m == 14 && zdepth == 2) rc = launch_z3<Z3InvA<SpecInt<14, true>, SpecInt<14, false>, 2, 2> >(z, stream);
+    else if (m == 14 && zdepth == 3) rc = launch_z3<Z3InvA<SpecInt<14, true>, SpecInt<14, false>, 2, 3> >(z, stream);
+    else if (env_int("DTCWT_B200_Z3_SPLIT", 0)) {
+        if (m == 10) rc = launch_z3<Z3InvS<SpecInt<10, true>, SpecInt<10, false>, 4> >(z, stream);
+        else if (m == 14) rc = launch_z3<Z3InvS<SpecInt<14, true>, SpecInt<14, false>, 4> >(z, stream);
+        else if (m == 16) rc = launch_z3<Z3InvS<SpecInt<16, true>, SpecInt<16, false>, 4> >(z, stream);
+        else rc = launch_z3<Z3InvS<SpecInt<18, true>, SpecInt<18, false>, 4> >(z, stream);
+    }
+    else if (m == 10) rc = launch_z3<Z3InvQ<10>::type>(z, stream);
     else if (m == 14 && env_int("DTCWT_B200_Z3_NG", 2) == 4) rc = launch_z3<Z3Inv<SpecInt<14, true>, SpecInt<14, false>, 4> >(z, stream);
     else if (m == 14) rc = launch_z3<Z3InvQ<14>::type>(z, stream);
     else if (m == 16) rc = launch_z3<Z3InvQ<16>::type>(z, stream);

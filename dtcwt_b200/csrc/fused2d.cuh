@@ -83,6 +83,27 @@ DTCWT_D F2 add2(const F2 a, const F2 b) {
 #endif
 }
 
+// Per-thread asynchronous copies global -> shared (cp.async, 8 bytes): a thread stages its own future inputs in a private slice
+// of shared memory and waits on its own copy groups; used by the kernels whose loads are per-thread 8-byte streams.
+DTCWT_D void async_copy8(void* smem_dst, const void* gmem_src) {
+#ifdef DTCWT_EMU
+    *reinterpret_cast<F2*>(smem_dst) = *reinterpret_cast<const F2*>(gmem_src);
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+#endif
+}
+DTCWT_D void async_commit() {
+#ifndef DTCWT_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+DTCWT_D void async_wait() {            // at most N of this thread's copy groups still pending
+#ifndef DTCWT_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
 DTCWT_HD constexpr int cmax(int a, int b) { return a > b ? a : b; }
 DTCWT_HD constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
@@ -949,6 +970,9 @@ struct Inv2d {
         const int qc = tid % QCOLS;
         const int t = tid / QCOLS;
         const int role = t % 2, strip = t / 2;                   // uniform within a warp
+        // quad columns right of the last window a stored output reads are nobody's input: on images narrower than a tile
+        // (the 128- and 64-wide slices of a 3-D level) that is up to two thirds of the threads
+        if (2 * ((TWI * bx - HLC) / 2 + qc) >= a.cols + HRC) return;
         const bool edge = (Q * GH * by - HLR < 0) || (Q * GH * (by + 1) + HRR > a.rows);      // rows only, see cols_body
         if (role == 0) {
             if (edge) cols_body<0, true>(a, sm, bx, by, bz, qc, strip);
@@ -998,6 +1022,7 @@ struct Inv2d {
             const int lp = 2 * (half / NSEG) + (task & 1), seg = half % NSEG;
             const int r = P * GH * by + 2 * lp - a.crop_r;             // first row of the pair
             if (r + 1 < 0 || r >= a.out_rows) continue;
+            if ((P / Q) * (TWI * bx + 4 * seg) - a.crop_c >= a.out_cols) continue;      // segment right of the image
             F2 acc[P * NGH];
 #pragma unroll
             for (int i = 0; i < P * NGH; ++i) acc[i] = zero2();
@@ -1044,6 +1069,7 @@ struct Inv2d {
             const int lr = task / NSEG, seg = task - lr * NSEG;
             const int r = P * GH * by + lr - a.crop_r;
             if (r < 0 || r >= a.out_rows) continue;
+            if ((P / Q) * (TWI * bx + 4 * seg) - a.crop_c >= a.out_cols) continue;      // segment right of the image
             float acc[P * NGH];
 #pragma unroll
             for (int i = 0; i < P * NGH; ++i) acc[i] = 0.f;

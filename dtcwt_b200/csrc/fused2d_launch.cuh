@@ -131,7 +131,7 @@ template <class K>
 __global__ void __launch_bounds__(kStreamThreads, K::kMinBlocks) invs1_kernel(const __grid_constant__ typename K::Args a) {
     const int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z, tid = threadIdx.x;
     typename K::Thread th;
-    K::init(a, th, bx, by, bz, tid);
+    K::init(a, th, bx, by, bz, tid, fused_smem);
     const int np = K::run_periods(a, by);
     for (int p = 0; p < np; ++p) {
         K::cols(a, th, fused_smem, bx, by, bz, tid, p);

@@ -86,11 +86,15 @@ struct InvS1Args {
 
 // DBG (diagnosis builds only, results are wrong): 1 = memory traffic without the arithmetic, 2 = arithmetic without the loads
 // HH: the second launch of a `_bp` level (transform2d.py:279-292): lowpass counted as zero, result ADDED to `out`
+// ASYNC > 0: the prefetched quad rows live in a thread-private slice of shared memory filled by cp.async (ASYNC stages of
+// four 8-byte copies per thread) instead of NST register stages: deeper prefetch at a lower register count, and still no
+// barrier -- a thread only ever waits on its own copy groups (fused2d.cuh: async_copy8 / async_wait).
 template <int K0, int K1, uint32_t M0, uint32_t M1, int RING_, int NST_, class T0 = ArgTaps, class T1 = ArgTaps, int MINB_ = 2, int DBG = 0,
-          bool HH = false>
+          bool HH = false, int ASYNC_ = 0>
 struct InvS1 {
     typedef InvS1Args Args;
-    static constexpr int RING = RING_, PER = RING_ / 2, NST = NST_;
+    static constexpr int ASYNC = ASYNC_;
+    static constexpr int RING = RING_, PER = RING_ / 2, NST = ASYNC_ > 0 ? ASYNC_ : NST_;
     static constexpr int C0 = (K0 - 1) / 2, C1 = (K1 - 1) / 2, CQ = round_up(C0, 2);
     static constexpr int kThreads = kStreamThreads;
     static constexpr int QC = kThreads / 2;                    // quad columns of a strip
@@ -100,8 +104,10 @@ struct InvS1 {
     static constexpr int NSEG = TWI / 8;                       // row task = 8 output columns of one row
     static constexpr int WS0 = (CQ - C0) / 4 * 4, WE0 = round_up(CQ + 8 + C0, 4);   // y1 window of a row task
     static constexpr int WS1 = (CQ - C1) / 4 * 4, WE1 = round_up(CQ + 8 + C1, 4);   // y2 window
-    static constexpr int kSmemFloats = 2 * RING * CYP;
+    static constexpr int kYFloats = 2 * RING * CYP;
+    static constexpr int kSmemFloats = kYFloats + (ASYNC_ > 0 ? ASYNC_ * 4 * 2 * kThreads : 0);      // y1 / y2 + the copy stages
     static constexpr int kMinBlocks = MINB_;
+    static_assert(ASYNC_ == 0 || DBG == 0, "diagnosis builds use the register stages");
     static_assert(K0 >= K1 && (K0 & 1) && (K1 & 1) && K0 <= kStreamMaxTaps && (M0 & 1u), "filter pair");
     static_assert(RING >= CQ + C0 + 1 && (RING % 2) == 0 && (PER % NST) == 0, "ring");
     static_assert(8 * (NSEG - 1) + WE0 <= CY && 8 * (NSEG - 1) + WE1 <= CY, "row-pass window inside the smem row");
@@ -109,10 +115,11 @@ struct InvS1 {
     struct Raw { F2 v[4]; };       // role 0: Z top row, Z bottom row, band 0, band 5;  role 1: bands 2, 3, 1, 4
     struct Thread {
         F2 acc[RING];
-        Raw st[NST];
+        Raw st[ASYNC_ > 0 ? 1 : NST];
         const char* ptr[4];        // byte addresses of this thread's column in quad row 0 of its four inputs
         int stride[4];             // bytes per quad row
         int fc;
+        F2* stage;                 // ASYNC: this thread's slice of the copy stages (element i of stage s at stage[(4 s + i) * kThreads])
     };
 
     static DTCWT_HD int run_rows(const Args& a) { return RING * a.periods; }
@@ -148,7 +155,24 @@ struct InvS1 {
         for (int i = 0; i < 4; ++i) r.v[i] = *reinterpret_cast<const F2*>(th.ptr[i] + (int64_t)q * th.stride[i]);   // one IMAD.WIDE
     }
 
-    static DTCWT_D void init(const Args& a, Thread& th, int bx, int by, int bz, int tid) {
+    // ASYNC: the four copies of quad row q into stage slot `slot`, one copy group
+    template <bool EDGE>
+    static DTCWT_D void issue_stage(const Args& a, const Thread& th, int slot, int q) {
+        if (EDGE) {
+            bool f;
+            q = fold_quad(q, a.rows / 2, f);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) async_copy8(th.stage + (4 * slot + i) * kThreads, th.ptr[i] + (int64_t)q * th.stride[i]);
+        async_commit();
+    }
+    static DTCWT_D void read_stage(const Thread& th, int slot, Raw& r) {
+        async_wait<NST - 1>();                                     // the oldest pending group has landed
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r.v[i] = th.stage[(4 * slot + i) * kThreads];
+    }
+
+    static DTCWT_D void init(const Args& a, Thread& th, int bx, int by, int bz, int tid, float* sm = nullptr) {
         const int qc = tid % QC, role = tid / QC;
         bool fc;
         const int gj = fold_quad((TWI * bx - CQ) / 2 + qc, a.cols / 2, fc);
@@ -170,8 +194,14 @@ struct InvS1 {
 #pragma unroll
         for (int i = 0; i < RING; ++i) th.acc[i] = zero2();
         const int q0 = quad_base(a, by, 0);
+        if (ASYNC > 0) {
+            th.stage = reinterpret_cast<F2*>(sm + kYFloats) + tid;
 #pragma unroll
-        for (int s = 0; s < NST; ++s) load_stage<true>(a, th, th.st[s], q0 + s);
+            for (int s = 0; s < NST; ++s) issue_stage<true>(a, th, s, q0 + s);
+            return;
+        }
+#pragma unroll
+        for (int s = 0; s < (ASYNC_ > 0 ? 1 : NST); ++s) load_stage<true>(a, th, th.st[s], q0 + s);
     }
 
     // c2q (transform2d.py:324-350), gains pre-scaled by 1/sqrt2:  top row (A, B), bottom row (C, D)
@@ -194,8 +224,14 @@ struct InvS1 {
         float* y = sm + ROLE * (RING * CYP) + 2 * qc;
 #pragma unroll
         for (int u = 0; u < PER; ++u) {
-            const Raw cur = th.st[u % NST];
-            load_stage<EDGE>(a, th, th.st[u % NST], qb + u + NST);
+            Raw cur;
+            if (ASYNC > 0) {
+                read_stage(th, u % NST, cur);
+                issue_stage<EDGE>(a, th, u % NST, qb + u + NST);       // refill the slot just read (same thread: program order)
+            } else {
+                cur = th.st[(ASYNC_ > 0 ? 0 : u % NST)];
+                load_stage<EDGE>(a, th, th.st[(ASYNC_ > 0 ? 0 : u % NST)], qb + u + NST);
+            }
             F2 at, ab, bt, bb;         // image A (filtered with g0) and image B (g1): top / bottom real rows
             if (ROLE == 0) {
                 at = cur.v[0]; ab = cur.v[1];
@@ -636,7 +672,7 @@ struct InvSq {
         for (int i = 0; i < 4; ++i) r.v[i] = *reinterpret_cast<const F2*>(th.ptr[i] + (int64_t)q * th.stride[i]);
     }
 
-    static DTCWT_D void init(const Args& a, Thread& th, int bx, int by, int bz, int tid) {
+    static DTCWT_D void init(const Args& a, Thread& th, int bx, int by, int bz, int tid, float* = nullptr) {
         const int qc = tid % QC, role = tid / QC;
         bool fc;
         const int gj = fold_quad((TWI * bx - HC) / 2 + qc, a.cols / 2, fc);

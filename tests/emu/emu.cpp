@@ -93,7 +93,7 @@ static int launch_invs1(typename K::Args& a, void* /*stream*/) {
         for (int by = 0; by < K::tiles_r(a); ++by)
             for (int bx = 0; bx < K::tiles_c(a); ++bx) {
                 for (size_t i = 0; i < sm.size(); ++i) sm[i] = NAN;
-                for (int tid = 0; tid < K::kThreads; ++tid) K::init(a, th[tid], bx, by, bz, tid);
+                for (int tid = 0; tid < K::kThreads; ++tid) K::init(a, th[tid], bx, by, bz, tid, sm.data());
                 const int np = K::run_periods(a, by);
                 for (int p = 0; p < np; ++p) {
                     for (int tid = 0; tid < K::kThreads; ++tid) K::cols(a, th[tid], sm.data(), bx, by, bz, tid, p);
