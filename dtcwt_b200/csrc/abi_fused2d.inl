@@ -129,6 +129,9 @@ template <int M> struct InvLqHH { typedef Inv2d<SpecInt<M, true>, SpecInt<M, fal
 // levels >= 2: q-shift pairs; every shipped family has a positive lowpass and a negative highpass tap correlation
 template <int M> struct FwdLq { typedef Fwd2d<SpecDec<M, true>, SpecDec<M, false>, 32, 16, 4> type; };
 template <int M> struct InvLq { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4> type; };
+// the same with the column pass's quad rows staged by per-thread cp.async (last argument: stages)
+template <int M> struct InvLqA { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4, false, false, RtPhase, RtPhase, false, 4> type; };
+template <int M> struct InvLqA2 { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4, false, false, RtPhase, RtPhase, false, 2> type; };
 // the same with the row pass on interleaved row pairs (all FFMA2); qshift_b: taps as immediates
 template <int M> struct InvLqP { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4, false, false, RtPhase, RtPhase, true> type; };
 typedef Inv2d<SpecInt<14, true>, SpecInt<14, false>, 4, 1, 4, false, false, BakedPhaseQ<QshiftB_g0>, BakedPhaseQ<QshiftB_g1>, true> InvLqP_qb;
@@ -390,6 +393,16 @@ int dtcwt_b200_inv2d_levelq_f32(const float* z, const float* yh, float* out, int
         if (m == 14) return launch_inv2d<InvLqP<14>::type>(a, stream);
         if (m == 16) return launch_inv2d<InvLqP<16>::type>(a, stream);
         return launch_inv2d<InvLqP<18>::type>(a, stream);
+    }
+    // stages of a per-thread cp.async prefetch in the column pass (0, the default: one quad row ahead in registers).  Measured
+    // SLOWER on this issue-bound kernel, 0.80 (4 stages) / 0.83 (2) vs 0.73 ms per 16 x 4096^2 step (profiles/r3_01): opt-in
+    const int nasync = env_int("DTCWT_B200_INVQ_ASYNC", 0);
+    if (nasync == 2 && m == 14) return launch_inv2d<InvLqA2<14>::type>(a, stream);
+    if (nasync > 0) {
+        if (m == 10) return launch_inv2d<InvLqA<10>::type>(a, stream);
+        if (m == 14) return launch_inv2d<InvLqA<14>::type>(a, stream);
+        if (m == 16) return launch_inv2d<InvLqA<16>::type>(a, stream);
+        return launch_inv2d<InvLqA<18>::type>(a, stream);
     }
     if (m == 10) return launch_inv2d<InvLq<10>::type>(a, stream);
     if (m == 14) return launch_inv2d<InvLq<14>::type>(a, stream);

@@ -16,6 +16,7 @@ static const int kFused3dMinSide = 32, kFused3dMinSideInv = 16;
 // slice kernels of the 3-D levels
 template <int M> struct FwdLqRaw { typedef Fwd2d<SpecDec<M, true>, SpecDec<M, false>, 32, 16, 4, RtPhase, RtPhase, RtPhase, kFwdRaw> type; };
 template <int M> struct InvLqRaw { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4, true> type; };
+template <int M> struct InvLqRawA { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4, true, false, RtPhase, RtPhase, false, 4> type; };   // cp.async stages
 // row pass on interleaved row pairs (fused2d.cuh: ROWPAIR); qshift_b with its taps as immediates
 template <int M> struct InvLqRawP { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4, true, false, RtPhase, RtPhase, true> type; };
 typedef Inv2d<SpecInt<14, true>, SpecInt<14, false>, 4, 1, 4, true, false, BakedPhaseQ<QshiftB_g0>, BakedPhaseQ<QshiftB_g1>, true> InvLqRawP_qb;
@@ -100,6 +101,10 @@ static int lowpass3d(const float* x, float* y, float* scratch, int64_t n, int64_
     ax.pad_lo = 0; ax.L = (int)d0; ax.Lout = (int)d0; ax.crop = 0; ax.accumulate = 0;
     const int KA = (m <= 7) ? 7 : (m <= 13 ? 13 : 19);
     taps_col(ax.t, h, m, KA, 1.0);
+    if (ax.L >= 128 && env_int("DTCWT_B200_AXIS_NG", 16) == 16) {      // long axes: 16 outputs per thread (abi_axis.inl)
+        if (KA == 13) return axis_launch_v<SpecCol<13>, 16>(ax, stream);
+        if (KA == 19) return axis_launch_v<SpecCol<19>, 16>(ax, stream);
+    }
     if (KA == 7) return axis_launch_v<SpecCol<7>, 8>(ax, stream);
     if (KA == 13) return axis_launch_v<SpecCol<13>, 8>(ax, stream);
     return axis_launch_v<SpecCol<19>, 8>(ax, stream);
@@ -276,6 +281,12 @@ int dtcwt_b200_inv3d_levelq_f32(const float* yl, const float* yh, float* out, fl
         if (m == 14) return launch_inv2d<InvLqRawP<14>::type>(a, stream);
         if (m == 16) return launch_inv2d<InvLqRawP<16>::type>(a, stream);
         return launch_inv2d<InvLqRawP<18>::type>(a, stream);
+    }
+    if (env_int("DTCWT_B200_INVQ_ASYNC", 0) > 0) {
+        if (m == 10) return launch_inv2d<InvLqRawA<10>::type>(a, stream);
+        if (m == 14) return launch_inv2d<InvLqRawA<14>::type>(a, stream);
+        if (m == 16) return launch_inv2d<InvLqRawA<16>::type>(a, stream);
+        return launch_inv2d<InvLqRawA<18>::type>(a, stream);
     }
     if (m == 10) return launch_inv2d<InvLqRaw<10>::type>(a, stream);
     if (m == 14) return launch_inv2d<InvLqRaw<14>::type>(a, stream);

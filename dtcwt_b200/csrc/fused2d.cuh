@@ -809,11 +809,14 @@ struct Inv2dArgs {
 // pass runs on pairs of rows with packed FFMA2 and scalar taps -- immediates when the taps are baked (TS0 / TS1), which
 // also takes the constant loads (LDCU) out of the column pass.  The kernel is issue-bound (profiles/r2_04: 74 % issue
 // active, a third of its instructions unpacked FFMA of the row pass), so halving the row pass's FMA instructions pays.
+// ASYNC > 0: the column pass stages its next ASYNC quad rows in a thread-private slice of shared memory with cp.async instead
+// of holding one prefetched quad row in registers (async_copy8 above): more loads in flight, no barrier.
 template <class G0, class G1, int NGV_, int NSTRIP_, int NWIDE_, bool RAW_ = false, bool HH_ = false, class TS0 = RtPhase,
-          class TS1 = RtPhase, bool ROWPAIR_ = false>
+          class TS1 = RtPhase, bool ROWPAIR_ = false, int ASYNC_ = 0>
 struct Inv2d {
     typedef Inv2dArgs Args;
     static constexpr bool RAW = RAW_, HH = HH_, ROWPAIR = ROWPAIR_;
+    static constexpr int ASYNC = ASYNC_;
     static_assert(!(ROWPAIR_ && HH_), "the accumulate-into-out variant keeps the single-row row pass");
     static constexpr int P = G0::P, Q = G0::Q;
     static constexpr int NGV = NGV_, NSTRIP = NSTRIP_, NWIDE = NWIDE_;
@@ -835,7 +838,7 @@ struct Inv2d {
     // ROWPAIR: pitch of a pair row (2 CY floats) padded by 4, so that adjacent pair rows sit one 16-byte bank group apart
     static constexpr int PYP = 2 * CY + 4;
     static constexpr int kImgFloats = ROWPAIR_ ? (RY / 2) * PYP : RY * CY;      // one of y1 / y2
-    static constexpr int kSmemFloats = 2 * kImgFloats;
+    static constexpr int kSmemFloats = 2 * kImgFloats + ASYNC_ * 4 * 2 * kFusedThreads;       // y1 / y2 + the copy stages
     static constexpr int kPhases = 2;
     static constexpr int kMinBlocks = 3;                                 // register budget: 3 CTAs (24 warps) per SM
     static_assert(P == G1::P && Q == G1::Q, "filter pair must share its rate");
@@ -869,6 +872,21 @@ struct Inv2d {
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) r.v[i] = *reinterpret_cast<const F2*>(ptr[i] + (int64_t)gi * stride[i]);
+    }
+
+    // ASYNC: the four copies of quad row `qrow` into one stage (element i at st[i * kThreads]), one copy group.  Quad rows
+    // that lie outside the image even after mirroring are copied from a clamped row and zeroed when they are read.
+    template <bool EDGE>
+    static DTCWT_D void issue_quad_row(const Args& a, const char* const (&ptr)[4], const int (&stride)[4], int qrow, F2* st) {
+        int gi = qrow;
+        if (EDGE) {
+            bool fr;
+            gi = reflect_quad(qrow, a.rows / 2, fr);
+            gi = gi < 0 ? 0 : (gi >= a.rows / 2 ? a.rows / 2 - 1 : gi);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) async_copy8(st + i * kThreads, ptr[i] + (int64_t)gi * stride[i]);
+        async_commit();
     }
 
     // c2q (transform2d.py:324-350), gains pre-scaled by 1/sqrt2:  top row (A, B), bottom row (C, D)
@@ -918,10 +936,34 @@ struct Inv2d {
 #pragma unroll
         for (int i = 0; i < NOUT; ++i) acc[i].x = acc[i].y = 0.f;
         Raw cur, nxt;
-        load_quad_row<EDGE>(a, ptr, stride, qr0, cur);
+        F2* stage = reinterpret_cast<F2*>(sm + 2 * kImgFloats) + (ROLE * NSTRIP + strip) * QCOLS + qc;      // + threadIdx.x
+        if (ASYNC > 0) {
+#pragma unroll
+            for (int d = 0; d < ASYNC; ++d)
+                if (d < NQR) issue_quad_row<EDGE>(a, ptr, stride, qr0 + d, stage + d * 4 * kThreads);
+        } else {
+            load_quad_row<EDGE>(a, ptr, stride, qr0, cur);
+        }
 #pragma unroll
         for (int jq = 0; jq < NQR; ++jq) {
-            if (jq + 1 < NQR) load_quad_row<EDGE>(a, ptr, stride, qr0 + jq + 1, nxt);
+            if (ASYNC > 0) {
+                F2* st = stage + (jq % (ASYNC > 0 ? ASYNC : 1)) * 4 * kThreads;
+                async_wait<(ASYNC > 0 ? ASYNC - 1 : 0)>();               // the oldest pending group -- quad row jq -- has landed
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cur.v[i] = st[i * kThreads];
+                if (EDGE) {
+                    bool fr;
+                    const int gi = reflect_quad(qr0 + jq, a.rows / 2, fr);
+                    if (!(gi >= 0 && gi < a.rows / 2)) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) cur.v[i].x = cur.v[i].y = 0.f;
+                    }
+                }
+                if (jq + ASYNC < NQR) issue_quad_row<EDGE>(a, ptr, stride, qr0 + jq + ASYNC, st);      // refill the slot just read
+                else async_commit();                                     // an empty group keeps the count uniform
+            } else if (jq + 1 < NQR) {
+                load_quad_row<EDGE>(a, ptr, stride, qr0 + jq + 1, nxt);
+            }
             F2 at, ab, bt, bb;         // image A (filtered with g0) and image B (g1): top / bottom real rows
             if (RAW) {
                 at = cur.v[0]; ab = cur.v[1]; bt = cur.v[2]; bb = cur.v[3];
@@ -947,7 +989,7 @@ struct Inv2d {
             fir_scatter<G1, NGV, HLR, TS1>(2 * jq, bt, a.g1, acc);
             fir_scatter<G0, NGV, HLR, TS0>(2 * jq + 1, ab, a.g0, acc);
             fir_scatter<G1, NGV, HLR, TS1>(2 * jq + 1, bb, a.g1, acc);
-            cur = nxt;
+            if (ASYNC == 0) cur = nxt;
         }
         if (ROWPAIR) {
             // pair row p = rows (2p, 2p+1): element (p, col, parity) at p * 2CY + 2 col + parity
