@@ -248,7 +248,7 @@ int dtcwt_b200_inv3d_levelq_f32(const float* yl, const float* yh, float* out, fl
     z.sub_stride = sub; z.vol_stride = od0 * a1 * a2;
     taps_int(z.lo, lo_a, lo_b, m, true, 0.5);
     taps_int(z.hi, hi_a, hi_b, m, false, 0.5);
-    const int zdepth = env_int("DTCWT_B200_Z3_ASYNC", 3);      // octets staged ahead by cp.async (0: plain loads, the round-2 kernel)
+    const int zdepth = env_int("DTCWT_B200_Z3_ASYNC", 2);      // octets staged ahead by cp.async (0: plain loads, the round-2 kernel)
     if (m == 14 && zdepth == 2) rc = launch_z3<Z3InvA<SpecInt<14, true>, SpecInt<14, false>, 2, 2> >(z, stream);
     else if (m == 14 && zdepth == 3) rc = launch_z3<Z3InvA<SpecInt<14, true>, SpecInt<14, false>, 2, 3> >(z, stream);
     else if (env_int("DTCWT_B200_Z3_SPLIT", 0)) {

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Assemble profiles/r2_04_end_of_round.md from the files a `tools/gpu/r2z.sh` run left in gpurun_out/ (bench lines,
-launch lists, ncu reports) and copy the evidence next to it.  usage: python tools/make_r2_report.py [TAG]"""
+"""Assemble profiles/<PREFIX>_end_of_round.md from the files a `tools/gpu/r2z.sh` / `r3z.sh` run left in gpurun_out/ (bench lines,
+launch lists, ncu reports or their on-box summaries) and copy the evidence next to it.
+usage: python tools/make_r2_report.py [TAG [PREFIX]]   (defaults: r2z r2_04)"""
 import json
 import os
 import shutil
@@ -11,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r2z"
+PREFIX = sys.argv[2] if len(sys.argv) > 2 else "r2_04"
 
 
 def load(name):
@@ -26,14 +28,14 @@ def run(cmd):
 
 
 def main():
-    out = ["# Round 2, end of round — measured state", "",
+    out = ["# Round 2, end of round — measured state (%s)" % TAG, "",
            "All numbers: 1x B200 of this pool unless stated, CUDA events, `tools/gpu/%s.sh` (smoke, `pytest -m gpu`, compute-sanitizer, "
            "the three bench lines with CPU baseline and e2e, launch lists, `ncu --set full`)." % TAG, ""]
-    copies = {"bench_%s.json" % TAG: "r2_04_bench_2d.json", "bench_%s_3d.json" % TAG: "r2_04_bench_3d.json",
-              "bench_%s_reg.json" % TAG: "r2_04_bench_reg.json", "bench_%s_defaults.json" % TAG: "r2_04_bench_near_sym_a_qshift_a.json",
-              "bench_%s_bp.json" % TAG: "r2_04_bench_near_sym_b_bp.json", "bench_%s_ref.json" % TAG: "r2_04_reference_arm_2d.json",
-              "launches_%s.csv" % TAG: "r2_04_launches_2d.csv", "launches_%s_3d.csv" % TAG: "r2_04_launches_3d.csv",
-              "sanitizer_memcheck_%s.log" % TAG: "r2_04_sanitizer_memcheck.log", "sanitizer_racecheck_%s.log" % TAG: "r2_04_sanitizer_racecheck.log"}
+    copies = {"bench_%s.json" % TAG: PREFIX + "_bench_2d.json", "bench_%s_3d.json" % TAG: PREFIX + "_bench_3d.json",
+              "bench_%s_reg.json" % TAG: PREFIX + "_bench_reg.json", "bench_%s_defaults.json" % TAG: PREFIX + "_bench_near_sym_a_qshift_a.json",
+              "bench_%s_bp.json" % TAG: PREFIX + "_bench_near_sym_b_bp.json", "bench_%s_ref.json" % TAG: PREFIX + "_reference_arm_2d.json",
+              "launches_%s.csv" % TAG: PREFIX + "_launches_2d.csv", "launches_%s_3d.csv" % TAG: PREFIX + "_launches_3d.csv",
+              "sanitizer_memcheck_%s.log" % TAG: PREFIX + "_sanitizer_memcheck.log", "sanitizer_racecheck_%s.log" % TAG: PREFIX + "_sanitizer_racecheck.log"}
     for src, dst in copies.items():
         if os.path.isfile(os.path.join(G, src)):
             shutil.copy(os.path.join(G, src), os.path.join(P, dst))
@@ -80,7 +82,10 @@ def main():
             out += ["## Launch list, %s (`ncu --metrics gpu__time_duration.sum`, 4 images / volumes, cold cache, serialised)" % title, "",
                     run([sys.executable, "tools/summarize_launches.py", csvf]).strip(), ""]
         rep = os.path.join(G, "prof_%s%s.ncu-rep" % (TAG, tag2))
-        if os.path.isfile(rep):
+        summ = os.path.join(G, "ncu_summary_%s%s.txt" % (TAG, tag2))
+        if os.path.isfile(summ):          # summarised on the GPU box (the report itself may not have travelled: 64 MiB limit)
+            out += ["## `ncu --set full`, one launch per kernel, %s" % title, "", "```", open(summ).read().strip(), "```", ""]
+        elif os.path.isfile(rep):
             out += ["## `ncu --set full`, one launch per kernel, %s" % title, "", "```", run([sys.executable, "tools/ncu_summary.py", rep]).strip(), "```", ""]
     rep = os.path.join(G, "prof_%s.ncu-rep" % TAG)
     if os.path.isfile(rep):
@@ -92,9 +97,13 @@ def main():
         if os.path.isfile(f):
             tail = [l for l in open(f).read().splitlines() if l.strip()][-3:]
             out += ["## compute-sanitizer --tool %s (subset of the GPU tests)" % name, "", "```"] + tail + ["```", ""]
-    with open(os.path.join(P, "r2_04_end_of_round.md"), "w") as f:
+    mix = os.path.join(G, "ncu_sass_mix_%s.txt" % TAG)
+    if os.path.isfile(mix):
+        out += ["## Executed-instruction mix and stall reasons per kernel (`tools/ncu_sass_mix.py`, source page of the 2-D report)", "", "```",
+                open(mix).read().strip(), "```", ""]
+    with open(os.path.join(P, PREFIX + "_end_of_round.md"), "w") as f:
         f.write("\n".join(out) + "\n")
-    print("wrote profiles/r2_04_end_of_round.md (%d lines)" % len(out))
+    print("wrote profiles/%s_end_of_round.md (%d lines)" % (PREFIX, len(out)))
 
 
 if __name__ == "__main__":
