@@ -1,6 +1,7 @@
 // C-ABI entry points of the registration / re-sampling kernels (registration.cuh).  Included after abi_generic.inl;
 // the including file provides  template <class Elem> int launch_1d(const typename Elem::Args&, void* stream).
 #ifdef DTCWT_EMIT_GENERIC
+#include <math.h>
 namespace dtcwt {
 
 static const double kExpectedShift = 3.14159265358979323846 / 2.15;
@@ -23,8 +24,12 @@ static int reg_qtilde_impl(const T* src, const T* ref, double* qt, int64_t n, in
     for (int b = 0; b < 6; ++b) {
         a.shift[b][0] = kExpectedShifts[b][0] * kExpectedShift;
         a.shift[b][1] = kExpectedShifts[b][1] * kExpectedShift;
+        for (int ax = 0; ax < 2; ++ax) {
+            a.rot[b][ax][0] = cos(-a.shift[b][ax]);
+            a.rot[b][ax][1] = sin(-a.shift[b][ax]);
+        }
     }
-    return launch_1d<QtildeElem<T> >(a, stream);
+    return launch_1d_2<QtildeElem<T> >(a, stream);
 }
 
 template <typename T>

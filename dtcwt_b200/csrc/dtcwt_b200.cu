@@ -30,6 +30,23 @@ static int launch_1d(const typename Elem::Args& a, void* stream) {
     return (int)cudaGetLastError();
 }
 
+// the same with two CTAs per SM asked of the compiler (register-heavy float64 elements: QtildeElem took 171 registers)
+template <class Elem>
+__global__ void __launch_bounds__(256, 2) generic_1d_kernel_2(const typename Elem::Args a, const int64_t total) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < total) Elem::run(a, gid);
+}
+
+template <class Elem>
+static int launch_1d_2(const typename Elem::Args& a, void* stream) {
+    const int64_t total = Elem::total(a);
+    if (total <= 0) return DTCWT_B200_OK;
+    const int64_t blocks = (total + 255) / 256;
+    if (blocks > 0x7fffffffLL) return DTCWT_B200_EUNSUPPORTED;
+    generic_1d_kernel_2<Elem><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, total);
+    return (int)cudaGetLastError();
+}
+
 template <class K>
 __global__ void __launch_bounds__(256) axis_kernel(const __grid_constant__ AxisArgs a, const int64_t total) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

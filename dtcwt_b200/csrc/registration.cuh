@@ -35,6 +35,20 @@ DTCWT_HD Cplx cadd(Cplx a, Cplx b) { a.re += b.re; a.im += b.im; return a; }
 DTCWT_HD double cabs2(Cplx a) { return a.re * a.re + a.im * a.im; }
 DTCWT_HD double cangle(Cplx a) { return atan2(a.im, a.re); }
 DTCWT_HD Cplx cexp(double ph) { Cplx r; r.re = cos(ph); r.im = sin(ph); return r; }
+// |z|^3 = s sqrt(s), s = |z|^2.  Device: single-precision reciprocal square root as the seed of one Newton step in double
+// (relative error ~1e-14) instead of the double-precision square root sequence -- 48 of them per pixel sat in Q~'s inner loop.
+DTCWT_HD double cabs3(Cplx a) {
+    const double s = cabs2(a);
+#if defined(__CUDA_ARCH__)
+    if (!(s > 1e-30 && s < 1e30)) return s * sqrt(s);           // zeros, denormals, overflow of the float seed
+    double r = (double)rsqrtf((float)s);
+    r = r * (1.5 - 0.5 * s * r * r);
+    r = r * (1.5 - 0.5 * s * r * r);
+    return s * (s * r);
+#else
+    return s * sqrt(s);
+#endif
+}
 
 // ------------------------------------------------------------------ Q~ matrices
 template <typename T>
@@ -47,6 +61,7 @@ struct QtildeArgs {
     int64_t r_n, r_band, r_row, r_col;     // complex strides of ref
     int reduce;
     double shift[6][2];             // EXPECTED_SHIFTS (registration.py:30)
+    double rot[6][2][2];            // exp(-i shift[band][axis]) as (re, im): the same for every pixel, prepared by the host
     double epsilon;
 };
 
@@ -79,13 +94,14 @@ struct QtildeElem {
                     const int y = clampi(i + dy, h), x = clampi(j + dx, w);
                     const Cplx uu = U(y, x), vv = V(y, x);
                     num = cadd(num, cmul(cconj(uu), vv));
-                    const double au = sqrt(cabs2(uu)), av = sqrt(cabs2(vv));
-                    den += au * au * au + av * av * av;
+                    den += cabs3(uu) + cabs3(vv);
                 }
             const double C = cabs2(num) / den;
             // phase gradients (registration.py:52-76): conjugate products across horizontal / vertical pairs, de-rotated
             // by the expected shift, averaged between the two pairs that straddle the pixel
-            const Cplx rot0 = cexp(-a.shift[band][0]), rot1 = cexp(-a.shift[band][1]);
+            Cplx rot0, rot1;
+            rot0.re = a.rot[band][0][0]; rot0.im = a.rot[band][0][1];
+            rot1.re = a.rot[band][1][0]; rot1.im = a.rot[band][1][1];
             auto Sx = [&](int x) {      // pair (x, x+1) of row i
                 return cmul(cadd(cmul(U(i, x + 1), cconj(U(i, x))), cmul(V(i, x + 1), cconj(V(i, x)))), rot0);
             };
@@ -112,10 +128,25 @@ struct QtildeElem {
             for (int r = 0; r < 6; ++r) Q[e++] += tmp[r] * tmp[6] * c2;
         }
         if (a.reduce) {
-#ifdef DTCWT_EMU
+#if defined(DTCWT_EMU) || !defined(__CUDA_ARCH__)
             for (int e = 0; e < 27; ++e) a.qt[b * 27 + e] += Q[e];
 #else
-            for (int e = 0; e < 27; ++e) atomicAdd(a.qt + b * 27 + e, Q[e]);
+            // sum over the image: first inside the warp (shuffles), then one atomic per warp and element -- 27 atomics per
+            // THREAD on the same 27 addresses made this launch ten times longer than the arithmetic (profiles/r3_01).
+            // A warp whose lanes belong to two images, or that is not full, falls back to per-thread atomics.
+            const unsigned act = __activemask();
+            const unsigned same = __match_any_sync(act, (int)b);
+            if (same == 0xffffffffu) {
+#pragma unroll
+                for (int e = 0; e < 27; ++e) {
+                    double v = Q[e];
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                    if ((threadIdx.x & 31) == 0) atomicAdd(a.qt + b * 27 + e, v);
+                }
+            } else {
+                for (int e = 0; e < 27; ++e) atomicAdd(a.qt + b * 27 + e, Q[e]);
+            }
 #endif
         } else {
             double* d = a.qt + gid * 27;
@@ -156,8 +187,10 @@ struct BoxRescaleElem {
         const double sx = ((double)a.w / (double)a.W) * ((double)X + 0.5) - 0.5;     // sampling.py:155-161
         const double sy = ((double)a.h / (double)a.H) * ((double)Y + 0.5) - 0.5;
         const double fx0 = floor(sx), fy0 = floor(sy), fx = sx - fx0, fy = sy - fy0;
-        const int x0 = reflect_coord(fx0, (int)a.w), x1 = reflect_coord(fx0 + 1.0, (int)a.w);
-        const int y0 = reflect_coord(fy0, (int)a.h), y1 = reflect_coord(fy0 + 1.0, (int)a.h);
+        // the rescale grid reaches at most one sample outside the array, where the half-sample symmetric extension
+        // (reflect_coord) is a clamp: no fmod per element
+        const int x0 = clampi((int)fx0, (int)a.w), x1 = clampi((int)fx0 + 1, (int)a.w);
+        const int y0 = clampi((int)fy0, (int)a.h), y1 = clampi((int)fy0 + 1, (int)a.h);
         const double lower = (1.0 - fx) * box(a, b, y0, x0, e) + fx * box(a, b, y0, x1, e);
         const double upper = (1.0 - fx) * box(a, b, y1, x0, e) + fx * box(a, b, y1, x1, e);
         const double v = (1.0 - fy) * lower + fy * upper;

@@ -72,8 +72,12 @@ def load():
         logging.warn = logging.warning
     if root not in sys.path:
         sys.path.insert(0, root)
-    import dtcwt  # noqa: E402
-    import dtcwt.numpy  # noqa: F401,E402
+    import warnings
+    with warnings.catch_warnings():
+        # the reference's docstrings hold '\p' style escapes: Python 3.12 reports each as a SyntaxWarning when it compiles them
+        warnings.simplefilter("ignore", SyntaxWarning)
+        import dtcwt  # noqa: E402
+        import dtcwt.numpy  # noqa: F401,E402
     return dtcwt
 
 

@@ -32,6 +32,9 @@ static int launch_1d(const typename Elem::Args& a, void* /*stream*/) {
     return DTCWT_B200_OK;
 }
 
+template <class Elem>
+static int launch_1d_2(const typename Elem::Args& a, void* stream) { return launch_1d<Elem>(a, stream); }
+
 template <class K>
 static int launch_axis(const AxisArgs& a, void* /*stream*/) {
     const int64_t total = K::total(a);
