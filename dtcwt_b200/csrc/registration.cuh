@@ -34,7 +34,21 @@ DTCWT_HD Cplx cconj(Cplx a) { a.im = -a.im; return a; }
 DTCWT_HD Cplx cadd(Cplx a, Cplx b) { a.re += b.re; a.im += b.im; return a; }
 DTCWT_HD double cabs2(Cplx a) { return a.re * a.re + a.im * a.im; }
 DTCWT_HD double cangle(Cplx a) { return atan2(a.im, a.re); }
-DTCWT_HD Cplx cexp(double ph) { Cplx r; r.re = cos(ph); r.im = sin(ph); return r; }
+DTCWT_HD Cplx cexp(double ph) {
+    Cplx r;
+#if defined(__CUDA_ARCH__)
+    sincos(ph, &r.im, &r.re);           // one argument reduction for both
+#else
+    r.re = cos(ph); r.im = sin(ph);
+#endif
+    return r;
+}
+// reflect_coord for a coordinate that is a whole number (every tap position of the samplers is): the same fold in integer
+// arithmetic -- no double-precision fmod per tap.  Falls back to reflect_coord for positions beyond the int range.
+DTCWT_HD int reflect_whole(double x, int n) {
+    if (!(x > -1.0e9 && x < 1.0e9)) return reflect_coord(x, n);
+    return reflect_any((int)x, n);
+}
 // |z|^3 = s sqrt(s), s = |z|^2.  Device: single-precision reciprocal square root as the seed of one Newton step in double
 // (relative error ~1e-14) instead of the double-precision square root sequence -- 48 of them per pixel sat in Q~'s inner loop.
 DTCWT_HD double cabs3(Cplx a) {
@@ -72,16 +86,11 @@ struct QtildeElem {
 
     static DTCWT_HD Cplx ld(const T* p, int64_t off) { Cplx c; c.re = (double)p[2 * off]; c.im = (double)p[2 * off + 1]; return c; }
 
-    static DTCWT_HD void run(const Args& a, int64_t gid) {
-        const int j = (int)(gid % a.w);
-        const int64_t t = gid / a.w;
-        const int i = (int)(t % a.h);
-        const int64_t b = t / a.h;
+    // Q += the contribution of one sub-band at pixel (i, j) of image b
+    static DTCWT_HD void add_band(const Args& a, int64_t b, int i, int j, int band, double (&Q)[27]) {
         const int h = (int)a.h, w = (int)a.w;
-        double Q[27];
-        for (int e = 0; e < 27; ++e) Q[e] = 0.0;
         const double xs = (double)j * (1.0 / (double)w), ys = (double)i * (1.0 / (double)h);
-        for (int band = 0; band < 6; ++band) {
+        {
             const T* u = a.src + 2 * (b * a.s_n + band * a.s_band);
             const T* v = a.ref + 2 * (b * a.r_n + band * a.r_band);
             auto U = [&](int y, int x) { return ld(u, (int64_t)y * a.s_row + (int64_t)x * a.s_col); };
@@ -127,6 +136,16 @@ struct QtildeElem {
                 for (int c = r; c < 6; ++c) Q[e++] += tmp[r] * tmp[c] * c2;
             for (int r = 0; r < 6; ++r) Q[e++] += tmp[r] * tmp[6] * c2;
         }
+    }
+
+    static DTCWT_HD void run(const Args& a, int64_t gid) {
+        const int j = (int)(gid % a.w);
+        const int64_t t = gid / a.w;
+        const int i = (int)(t % a.h);
+        const int64_t b = t / a.h;
+        double Q[27];
+        for (int e = 0; e < 27; ++e) Q[e] = 0.0;
+        for (int band = 0; band < 6; ++band) add_band(a, b, i, j, band, Q);
         if (a.reduce) {
 #if defined(DTCWT_EMU) || !defined(__CUDA_ARCH__)
             for (int e = 0; e < 27; ++e) a.qt[b * 27 + e] += Q[e];
@@ -302,7 +321,7 @@ struct SampleElem {
     }
 
     static DTCWT_HD Cplx tap(const Args& a, int64_t b, int c, double fx, double fy) {
-        const int x = reflect_coord(fx, (int)a.w), y = reflect_coord(fy, (int)a.h);
+        const int x = reflect_whole(fx, (int)a.w), y = reflect_whole(fy, (int)a.h);       // fx, fy are whole numbers
         const T* p = a.im + a.ncomp * (b * a.i_n + (int64_t)y * a.i_y + (int64_t)x * a.i_x + (int64_t)c * a.i_c);
         Cplx v;
         v.re = (double)p[0];
