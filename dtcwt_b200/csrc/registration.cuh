@@ -210,8 +210,28 @@ struct BoxRescaleElem {
         // (reflect_coord) is a clamp: no fmod per element
         const int x0 = clampi((int)fx0, (int)a.w), x1 = clampi((int)fx0 + 1, (int)a.w);
         const int y0 = clampi((int)fy0, (int)a.h), y1 = clampi((int)fy0 + 1, (int)a.h);
-        const double lower = (1.0 - fx) * box(a, b, y0, x0, e) + fx * box(a, b, y0, x1, e);
-        const double upper = (1.0 - fx) * box(a, b, y1, x0, e) + fx * box(a, b, y1, x1, e);
+        double b00, b01, b10, b11;
+        if (x1 == x0 + 1 && y1 == y0 + 1) {
+            // the four 3 x 3 windows overlap in a 4 x 4 patch: 16 loads instead of 36, the same additions in the same order
+            const int h = (int)a.h, w = (int)a.w;
+            const int64_t c0 = (int64_t)clampi(x0 - 1, w) * 27, c1 = (int64_t)x0 * 27, c2 = (int64_t)x1 * 27, c3 = (int64_t)clampi(x1 + 1, w) * 27;
+            const int ys[4] = {clampi(y0 - 1, h), y0, y1, clampi(y1 + 1, h)};
+            double ra[4], rb[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double* p = a.qt + ((b * a.h + ys[r]) * a.w) * 27 + e;
+                const double q0 = p[c0], q1 = p[c1], q2 = p[c2], q3 = p[c3];
+                ra[r] = (q0 + q1 + q2) / 3.0;
+                rb[r] = (q1 + q2 + q3) / 3.0;
+            }
+            b00 = (ra[0] + ra[1] + ra[2]) / 3.0; b01 = (rb[0] + rb[1] + rb[2]) / 3.0;
+            b10 = (ra[1] + ra[2] + ra[3]) / 3.0; b11 = (rb[1] + rb[2] + rb[3]) / 3.0;
+        } else {
+            b00 = box(a, b, y0, x0, e); b01 = box(a, b, y0, x1, e);
+            b10 = box(a, b, y1, x0, e); b11 = box(a, b, y1, x1, e);
+        }
+        const double lower = (1.0 - fx) * b00 + fx * b01;
+        const double upper = (1.0 - fx) * b10 + fx * b11;
         const double v = (1.0 - fy) * lower + fy * upper;
         if (a.accumulate) a.out[gid] += v; else a.out[gid] = v;
     }
