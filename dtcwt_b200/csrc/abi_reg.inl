@@ -29,7 +29,7 @@ static int reg_qtilde_impl(const T* src, const T* ref, double* qt, int64_t n, in
             a.rot[b][ax][1] = sin(-a.shift[b][ax]);
         }
     }
-    return launch_1d_2<QtildeElem<T> >(a, stream);
+    return launch_qtilde<T>(a, stream);
 }
 
 template <typename T>

@@ -47,6 +47,23 @@ static int launch_1d_2(const typename Elem::Args& a, void* stream) {
     return (int)cudaGetLastError();
 }
 
+// Q~ of the registration (registration.cuh): two lanes per pixel, three sub-bands each; every thread of the grid takes part in
+// the shuffles (lanes beyond the last pixel carry zeros)
+template <class T>
+__global__ void __launch_bounds__(256, 2) qtilde_kernel(const QtildeArgs<T> a) {
+    QtildeElem<T>::run_lanes(a, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+template <class T>
+static int launch_qtilde(const QtildeArgs<T>& a, void* stream) {
+    const int64_t total = QtildeElem<T>::total(a);
+    if (total <= 0) return DTCWT_B200_OK;
+    const int64_t blocks = (2 * total + 255) / 256;
+    if (blocks > 0x7fffffffLL) return DTCWT_B200_EUNSUPPORTED;
+    qtilde_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
 template <class K>
 __global__ void __launch_bounds__(256) axis_kernel(const __grid_constant__ AxisArgs a, const int64_t total) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -138,6 +138,52 @@ struct QtildeElem {
         }
     }
 
+#if !defined(DTCWT_EMU) && defined(__CUDACC__)
+    // Device launch shape (dtcwt_b200.cu: qtilde_kernel): TWO adjacent lanes per pixel with three sub-bands each -- twice the
+    // threads for the coarse pyramid levels, whose few hundred CTAs of long dependent float64 chains do not fill the GPU, and
+    // half the chain per thread.  The two lanes add their 27 values with one shuffle; each then writes every other element
+    // (or feeds the image-wide reduction).  Every thread of the grid takes part; lanes beyond the last pixel carry zeros.
+    static __device__ __forceinline__ void run_lanes(const Args& a, int64_t gid2) {
+        const int half = (int)(gid2 & 1);
+        const int64_t gid = gid2 >> 1;
+        const bool live = gid < total(a);
+        const int64_t g = live ? gid : 0;
+        const int j = (int)(g % a.w);
+        const int64_t t = g / a.w;
+        const int i = (int)(t % a.h);
+        const int64_t b = t / a.h;
+        double Q[27];
+#pragma unroll
+        for (int e = 0; e < 27; ++e) Q[e] = 0.0;
+        if (live)
+            for (int band = 3 * half; band < 3 * half + 3; ++band) add_band(a, b, i, j, band, Q);
+        // (b0 + b1 + b2) + (b3 + b4 + b5): float64, differs from the reference's sequential sum in the last bits only
+#pragma unroll
+        for (int e = 0; e < 27; ++e) Q[e] += __shfl_xor_sync(0xffffffffu, Q[e], 1);
+        if (a.reduce) {
+            // image-wide sum: the sixteen pixels of a warp, then one atomic per warp and element
+            const unsigned same = __match_any_sync(0xffffffffu, live ? (int)b : -1);
+            if (same == 0xffffffffu) {
+#pragma unroll
+                for (int e = 0; e < 27; ++e) {
+                    double v = Q[e];
+#pragma unroll
+                    for (int off = 2; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                    if ((threadIdx.x & 31) == 0 && live) atomicAdd(a.qt + b * 27 + e, v);
+                }
+            } else if (live && half == 0) {
+                for (int e = 0; e < 27; ++e) atomicAdd(a.qt + b * 27 + e, Q[e]);
+            }
+            return;
+        }
+        if (!live) return;
+        double* d = a.qt + gid * 27;
+#pragma unroll
+        for (int e = 0; e < 27; ++e)
+            if ((e & 1) == half) d[e] = Q[e];
+    }
+#endif
+
     static DTCWT_HD void run(const Args& a, int64_t gid) {
         const int j = (int)(gid % a.w);
         const int64_t t = gid / a.w;

@@ -34,6 +34,8 @@ static int launch_1d(const typename Elem::Args& a, void* /*stream*/) {
 
 template <class Elem>
 static int launch_1d_2(const typename Elem::Args& a, void* stream) { return launch_1d<Elem>(a, stream); }
+template <class T>
+static int launch_qtilde(const QtildeArgs<T>& a, void* stream) { return launch_1d<QtildeElem<T> >(a, stream); }   // one thread per pixel on the host
 
 template <class K>
 static int launch_axis(const AxisArgs& a, void* /*stream*/) {
