@@ -50,7 +50,11 @@ static int sample_impl(const T* im, T* out, const double* xs, const double* ys, 
     a.i_n = i_n; a.i_y = i_y; a.i_x = i_x; a.i_c = i_c; a.o_n = o_n; a.o_y = o_y; a.o_x = o_x; a.o_c = o_c;
     a.coord_n = coord_n;
     a.ncomp = is_complex ? 2 : 1; a.method = method; a.coords = coords; a.phase = wx ? 1 : 0;
-    for (int c = 0; c < 8; ++c) { a.wx[c] = (wx && c < C) ? wx[c] : 0.0; a.wy[c] = (wy && c < C) ? wy[c] : 0.0; }
+    for (int c = 0; c < 8; ++c) {
+        a.wx[c] = (wx && c < C) ? wx[c] : 0.0; a.wy[c] = (wy && c < C) ? wy[c] : 0.0;
+        a.rx[c][0] = cos(-a.wx[c]); a.rx[c][1] = sin(-a.wx[c]);
+        a.ry[c][0] = cos(-a.wy[c]); a.ry[c][1] = sin(-a.wy[c]);
+    }
     return launch_1d<SampleElem<T> >(a, stream);
 }
 

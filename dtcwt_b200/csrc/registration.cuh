@@ -373,6 +373,7 @@ struct SampleArgs {
     int coords;                     // 0: xs / ys arrays; 1: rescale to [oh][ow] (sampling.py:155-161)
     int phase;                      // sample_highpass / rescale_highpass (sampling.py:192-278): un-roll, sample, re-roll
     double wx[8], wy[8];            // phase advance per channel (DTHETA_DX_2D / DTHETA_DY_2D of the selected sub-bands)
+    double rx[8][2], ry[8][2];      // exp(-i wx[c]), exp(-i wy[c]) as (re, im), prepared by the host
 };
 
 template <typename T>
@@ -384,6 +385,14 @@ struct SampleElem {
         if (x == 0.0) return 1.0;
         const double pi = 3.14159265358979323846, px = pi * x;
         return (sin(px) / px) * (sin(px / 3.0) / (px / 3.0));
+    }
+
+    static DTCWT_HD Cplx raw(const Args& a, int64_t b, int c, int x, int y) {      // the stored sample, no phase handling
+        const T* p = a.im + a.ncomp * (b * a.i_n + (int64_t)y * a.i_y + (int64_t)x * a.i_x + (int64_t)c * a.i_c);
+        Cplx v;
+        v.re = (double)p[0];
+        v.im = a.ncomp == 2 ? (double)p[1] : 0.0;
+        return v;
     }
 
     static DTCWT_HD Cplx tap(const Args& a, int64_t b, int c, double fx, double fy) {
@@ -416,8 +425,25 @@ struct SampleElem {
             acc = tap(a, b, c, rint(sx), rint(sy));                      // np.round: half to even
         } else if (a.method == kSampleBilinear) {
             const double fx0 = floor(sx), fy0 = floor(sy), fx = sx - fx0, fy = sy - fy0;
-            const Cplx p00 = tap(a, b, c, fx0, fy0), p10 = tap(a, b, c, fx0 + 1.0, fy0);
-            const Cplx p01 = tap(a, b, c, fx0, fy0 + 1.0), p11 = tap(a, b, c, fx0 + 1.0, fy0 + 1.0);
+            Cplx p00, p10, p01, p11;
+            if (a.phase) {
+                // phase un-rolling of the four taps: one sincos for the first, the neighbours by the angle-addition
+                // theorem (a complex multiply with the per-channel constants exp(-i wx), exp(-i wy)) wherever the mirrored
+                // coordinates are still adjacent -- everywhere except on the image border
+                const int x0 = reflect_whole(fx0, (int)a.w), x1 = reflect_whole(fx0 + 1.0, (int)a.w);
+                const int y0 = reflect_whole(fy0, (int)a.h), y1 = reflect_whole(fy0 + 1.0, (int)a.h);
+                Cplx rx, ry;
+                rx.re = a.rx[c][0]; rx.im = a.rx[c][1]; ry.re = a.ry[c][0]; ry.im = a.ry[c][1];
+                const Cplx e00 = cexp(-(a.wx[c] * (double)x0 + a.wy[c] * (double)y0));
+                const Cplx e10 = (x1 == x0 + 1) ? cmul(e00, rx) : cexp(-(a.wx[c] * (double)x1 + a.wy[c] * (double)y0));
+                const Cplx e01 = (y1 == y0 + 1) ? cmul(e00, ry) : cexp(-(a.wx[c] * (double)x0 + a.wy[c] * (double)y1));
+                const Cplx e11 = (y1 == y0 + 1) ? cmul(e10, ry) : cexp(-(a.wx[c] * (double)x1 + a.wy[c] * (double)y1));
+                p00 = cmul(raw(a, b, c, x0, y0), e00); p10 = cmul(raw(a, b, c, x1, y0), e10);
+                p01 = cmul(raw(a, b, c, x0, y1), e01); p11 = cmul(raw(a, b, c, x1, y1), e11);
+            } else {
+                p00 = tap(a, b, c, fx0, fy0); p10 = tap(a, b, c, fx0 + 1.0, fy0);
+                p01 = tap(a, b, c, fx0, fy0 + 1.0); p11 = tap(a, b, c, fx0 + 1.0, fy0 + 1.0);
+            }
             const double lr = (1.0 - fx) * p00.re + fx * p10.re, li = (1.0 - fx) * p00.im + fx * p10.im;
             const double ur = (1.0 - fx) * p01.re + fx * p11.re, ui = (1.0 - fx) * p01.im + fx * p11.im;
             acc.re = (1.0 - fy) * lr + fy * ur;
