@@ -155,6 +155,7 @@ static int fwd_common(Fwd2dArgs& a, const float* x, float* lolo, float* yh, int6
     a.out_rows = P * a.Lr / Q; a.out_cols = P * a.Lc / Q;
     a.zs_n = zs_n; a.zs_band = zs_band; a.zs_row = zs_row;
     a.use_tma = 0;
+    a.prefetch = 0;
     return DTCWT_B200_OK;
 }
 

@@ -47,6 +47,7 @@ static int slices_fwd(Fwd2dArgs& a, const float* x, float* out, int64_t slices, 
     a.out_rows = P * a.Lr / Q; a.out_cols = P * a.Lc / Q;
     a.zs_n = 0; a.zs_band = sub_stride; a.zs_row = 0;
     a.use_tma = 0;
+    a.prefetch = 0;
     return DTCWT_B200_OK;
 }
 

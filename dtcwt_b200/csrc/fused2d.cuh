@@ -262,6 +262,7 @@ struct Fwd2dArgs {
     int Lr, Lc;                     // logical (padded) size
     int out_rows, out_cols;         // P*Lr/Q, P*Lc/Q
     int use_tma;
+    int prefetch;                   // one CTA per tile: L2 prefetch of the tile this many tiles ahead (0: none), see fwd2d_kernel
     int64_t zs_n, zs_band, zs_row;
     PhaseTaps h0, h1s;              // row pass: lowpass, highpass/sqrt2
     PhaseTaps v0, v1, v1s;          // column pass: lowpass, highpass, highpass/sqrt2
