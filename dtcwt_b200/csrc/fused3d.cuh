@@ -125,18 +125,19 @@ struct Z3Fwd {
 #pragma unroll
         for (int q = 0; q < NOUT / 2; ++q) {
             if (zo + 2 * q < Lout) {
-                const float A = y[0][2 * q].x, E = y[0][2 * q].y, B = y[1][2 * q].x, F = y[1][2 * q].y;
-                const float C = y[0][2 * q + 1].x, G = y[0][2 * q + 1].y, D = y[1][2 * q + 1].x, H = y[1][2 * q + 1].y;
+                // with X = (A, E), Y = (-G, C), Z = (D, H), W = (-F, B) as float pairs:
+                //   p = X + Y - Z + W   q = X + Y + Z - W   r = X - Y + Z + W   s = X - Y - Z - W
+                // (eight packed additions instead of 24 scalar ones; they associate differently, which moves the last bit)
+                const F2 X = y[0][2 * q], Z = y[1][2 * q + 1];
+                F2 Y, W;
+                Y.x = -y[0][2 * q + 1].y; Y.y = y[0][2 * q + 1].x;
+                W.x = -y[1][2 * q].y; W.y = y[1][2 * q].x;
+                const F2 u1 = add2(X, Y), u2 = fma2(-1.f, Y, X), v1 = fma2(-1.f, W, Z), v2 = add2(Z, W);
                 float* zz = z + 2 * (int64_t)q * a.zs_0;
-                F2 c;
-                c.x = A - G - D - F; c.y = B - H + C + E;
-                *reinterpret_cast<F2*>(zz) = c;                                   // p
-                c.x = A - G + D + F; c.y = -B + H + C + E;
-                *reinterpret_cast<F2*>(zz + cs) = c;                              // q
-                c.x = A + G + D - F; c.y = B + H - C + E;
-                *reinterpret_cast<F2*>(zz + 2 * cs) = c;                          // r
-                c.x = A + G - D + F; c.y = -B - H - C + E;
-                *reinterpret_cast<F2*>(zz + 3 * cs) = c;                          // s
+                *reinterpret_cast<F2*>(zz) = fma2(-1.f, v1, u1);                  // p
+                *reinterpret_cast<F2*>(zz + cs) = add2(u1, v1);                   // q
+                *reinterpret_cast<F2*>(zz + 2 * cs) = add2(u2, v2);               // r
+                *reinterpret_cast<F2*>(zz + 3 * cs) = fma2(-1.f, v2, u2);         // s
             }
         }
     }
@@ -535,15 +536,18 @@ struct Z3InvA {
         for (int i = 0; i < 4; ++i) async_copy8(st + (4 + i) * kThreads, ph + i * s.cs);
     }
 
+    // c2cube on complex values as float pairs: with u = p + q, v = r + s, w = q - p, z = s - r (packed adds, FADD2)
+    //   (A, E) = u + v     (G, -C) = v - u     (D, H) = w - z     (F, -B) = w + z
+    // eight packed additions and two sign flips instead of 24 scalar additions (the kernel is issue-bound once its loads are
+    // staged); the sums associate differently from the scalar form, which only moves the last bit
+    static DTCWT_D F2 sub2(const F2 a, const F2 b) { return fma2(-1.f, b, a); }      // a - b, exact: one FFMA2
     static DTCWT_D void unpack_vals(const F2 p, const F2 q, const F2 r, const F2 s, typename Base::Oct& o) {
-        o.v[0][0].x = p.x + q.x + r.x + s.x;        // A
-        o.v[0][0].y = p.y + q.y + r.y + s.y;        // E
-        o.v[0][1].x = p.y - q.y + r.y - s.y;        // B
-        o.v[0][1].y = -p.x + q.x - r.x + s.x;       // F
-        o.v[1][0].x = p.y + q.y - r.y - s.y;        // C
-        o.v[1][0].y = -p.x - q.x + r.x + s.x;       // G
-        o.v[1][1].x = -p.x + q.x + r.x - s.x;       // D
-        o.v[1][1].y = -p.y + q.y + r.y - s.y;       // H
+        const F2 u = add2(p, q), v = add2(r, s), w = sub2(q, p), z = sub2(s, r);
+        const F2 ae = add2(u, v), gc = sub2(v, u), dh = sub2(w, z), fb = add2(w, z);
+        o.v[0][0] = ae;                              // A, E
+        o.v[0][1].x = -fb.y; o.v[0][1].y = fb.x;     // B, F
+        o.v[1][0].x = -gc.y; o.v[1][0].y = gc.x;     // C, G
+        o.v[1][1] = dh;                              // D, H
     }
 
     static DTCWT_D void run(const Args& a, int64_t gid) {
