@@ -124,6 +124,7 @@ typedef InvS1<7, 5, 0x7fu, 0x1fu, 8, 2> InvL1_7_5;                  // near_sym_
 // `_bp` families: the second launch of a level, bands 1 and 4 from the band-pass pair (h2 / g2) in the H1 / G1 slot
 typedef Fwd2d<SpecCol<19>, SpecCol<19>, 64, 64, 8, RtPhase, RtPhase, RtPhase, kFwdHH> FwdT1_hh;
 typedef InvS1<19, 19, 0x7ffffu, 0x7ffffu, 24, 3, ArgTaps, ArgTaps, 2, 0, true> InvL1_hh;
+typedef InvS1<19, 19, 0x7ffffu, 0x7ffffu, 24, 3, ArgTaps, ArgTaps, 2, 0, true, 6> InvL1_hhA;      // cp.async stages (no spills at 128 registers)
 template <int M> struct FwdLqHH { typedef Fwd2d<SpecDec<M, true>, SpecDec<M, false>, 32, 16, 4, RtPhase, RtPhase, RtPhase, kFwdHH> type; };
 template <int M> struct InvLqHH { typedef Inv2d<SpecInt<M, true>, SpecInt<M, false>, 4, 1, 4, false, true> type; };
 // levels >= 2: q-shift pairs; every shipped family has a positive lowpass and a negative highpass tap correlation
@@ -544,6 +545,7 @@ int dtcwt_b200_inv2d_level1_hh_f32(const float* yh, float* out, int64_t n, int64
     pair_tab(a.p0, a.g0, 19);
     pair_tab(a.p1, a.g1, 19);
     a.periods = choose_periods(a.rows, InvL1_hh::RING, (int64_t)InvL1_hh::tiles_c(a) * a.n);
+    if (env_int("DTCWT_B200_INV_ASYNC", 6) > 0) return launch_invs1<InvL1_hhA>(a, stream);
     return launch_invs1<InvL1_hh>(a, stream);
 }
 #endif  // DTCWT_EMIT_INV2D_1

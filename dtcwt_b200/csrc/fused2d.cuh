@@ -872,7 +872,7 @@ struct Inv2d {
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) r.v[i] = *reinterpret_cast<const F2*>(ptr[i] + (int64_t)gi * stride[i]);
+        for (int i = (HH ? 2 : 0); i < 4; ++i) r.v[i] = *reinterpret_cast<const F2*>(ptr[i] + (int64_t)gi * stride[i]);
     }
 
     // ASYNC: the four copies of quad row `qrow` into one stage (element i at st[i * kThreads]), one copy group.  Quad rows
@@ -904,6 +904,9 @@ struct Inv2d {
 
     template <int ROLE, bool EDGE>
     static DTCWT_D void cols_body(const Args& a, float* sm, int bx, int by, int bz, int qc, int strip) {
+        // HH (band-pass launch of a `_bp` level): the lowpass and the sub-bands 0, 5, 2, 3 count as zero -- role 0 has no work,
+        // role 1 filters c2q(bands 1, 4) with the band-pass pair only, the row pass reads y2 only
+        if (HH && ROLE == 0) return;
         // Columns: strips on the left / right border mirror their outer quad columns (fc: swap the two columns of the
         // quad); quad columns further out feed outputs that are never stored and are clamped.  `cedge` is uniform over the
         // CTA, so interior strips skip the swaps with one branch -- keeping border strips on the same code as interior
@@ -973,7 +976,8 @@ struct Inv2d {
                 if (HH) { at = zero2(); ab = zero2(); }
                 c2q_rows(cur.v[2], cur.v[3], ga0, ga1, bt, bb);
             } else {
-                c2q_rows(cur.v[0], cur.v[1], ga0, ga1, at, ab);
+                if (HH) { at = zero2(); ab = zero2(); }
+                else c2q_rows(cur.v[0], cur.v[1], ga0, ga1, at, ab);
                 c2q_rows(cur.v[2], cur.v[3], gb0, gb1, bt, bb);
             }
             if (EDGE) {
@@ -986,9 +990,9 @@ struct Inv2d {
                 flip_quad(false, fc, at, ab);
                 flip_quad(false, fc, bt, bb);
             }
-            fir_scatter<G0, NGV, HLR, TS0>(2 * jq, at, a.g0, acc);
+            if (!HH) fir_scatter<G0, NGV, HLR, TS0>(2 * jq, at, a.g0, acc);
             fir_scatter<G1, NGV, HLR, TS1>(2 * jq, bt, a.g1, acc);
-            fir_scatter<G0, NGV, HLR, TS0>(2 * jq + 1, ab, a.g0, acc);
+            if (!HH) fir_scatter<G0, NGV, HLR, TS0>(2 * jq + 1, ab, a.g0, acc);
             fir_scatter<G1, NGV, HLR, TS1>(2 * jq + 1, bb, a.g1, acc);
             if (ASYNC == 0) cur = nxt;
         }
@@ -1117,7 +1121,7 @@ struct Inv2d {
 #pragma unroll
             for (int i = 0; i < P * NGH; ++i) acc[i] = 0.f;
             float w[WN];
-            {
+            if (!HH) {
                 const F4* src = reinterpret_cast<const F4*>(y1 + lr * CY + seg * 4);
 #pragma unroll
                 for (int c = 0; c < WN / 4; ++c) {

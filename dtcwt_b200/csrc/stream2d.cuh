@@ -119,8 +119,10 @@ struct InvS1 {
         const char* ptr[4];        // byte addresses of this thread's column in quad row 0 of its four inputs
         int stride[4];             // bytes per quad row
         int fc;
+        int idle;                  // HH: role 0 (lowpass + bands 0, 5: all zero in the band-pass launch) has nothing to do
         F2* stage;                 // ASYNC: this thread's slice of the copy stages (element i of stage s at stage[(4 s + i) * kThreads])
     };
+    static_assert(!HH || K0 == K1, "HH: the band-pass filter sits in both slots (first touch of a ring row comes from it)");
 
     static DTCWT_HD int run_rows(const Args& a) { return RING * a.periods; }
     static DTCWT_HD int tiles_c(const Args& a) { return (a.cols + TWI - 1) / TWI; }
@@ -151,25 +153,29 @@ struct InvS1 {
             for (int i = 0; i < 4; ++i) { r.v[i].x = (float)q; r.v[i].y = (float)(q + i); }
             return;
         }
+        if (HH && th.idle) return;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) r.v[i] = *reinterpret_cast<const F2*>(th.ptr[i] + (int64_t)q * th.stride[i]);   // one IMAD.WIDE
+        for (int i = (HH ? 2 : 0); i < 4; ++i) r.v[i] = *reinterpret_cast<const F2*>(th.ptr[i] + (int64_t)q * th.stride[i]);   // one IMAD.WIDE
     }
 
-    // ASYNC: the four copies of quad row q into stage slot `slot`, one copy group
+    // ASYNC: the four copies of quad row q into stage slot `slot`, one copy group (HH: only bands 1 and 4 of role 1)
     template <bool EDGE>
     static DTCWT_D void issue_stage(const Args& a, const Thread& th, int slot, int q) {
         if (EDGE) {
             bool f;
             q = fold_quad(q, a.rows / 2, f);
         }
+        if (!(HH && th.idle)) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) async_copy8(th.stage + (4 * slot + i) * kThreads, th.ptr[i] + (int64_t)q * th.stride[i]);
+            for (int i = (HH ? 2 : 0); i < 4; ++i)
+                async_copy8(th.stage + (4 * slot + i) * kThreads, th.ptr[i] + (int64_t)q * th.stride[i]);
+        }
         async_commit();
     }
     static DTCWT_D void read_stage(const Thread& th, int slot, Raw& r) {
         async_wait<NST - 1>();                                     // the oldest pending group has landed
 #pragma unroll
-        for (int i = 0; i < 4; ++i) r.v[i] = th.stage[(4 * slot + i) * kThreads];
+        for (int i = (HH ? 2 : 0); i < 4; ++i) r.v[i] = th.stage[(4 * slot + i) * kThreads];
     }
 
     static DTCWT_D void init(const Args& a, Thread& th, int bx, int by, int bz, int tid, float* sm = nullptr) {
@@ -177,6 +183,7 @@ struct InvS1 {
         bool fc;
         const int gj = fold_quad((TWI * bx - CQ) / 2 + qc, a.cols / 2, fc);
         th.fc = fc ? 1 : 0;
+        th.idle = (HH && role == 0) ? 1 : 0;
         const float* zimg = a.z + (int64_t)bz * a.rows * a.cols + 2 * gj;
         const float* yb = a.yh + 2 * ((int64_t)bz * a.zs_n + gj);
         const int sz = 8 * a.cols, sb = 8 * (int)a.zs_row;       // bytes per quad row (the ABI bounds both)
@@ -217,6 +224,9 @@ struct InvS1 {
 
     template <int ROLE, bool EDGE>
     static DTCWT_D void cols_role(const Args& a, Thread& th, float* sm, int by, int p, int qc, bool cedge) {
+        // HH (the band-pass launch of a `_bp` level): the lowpass and the sub-bands 0, 5, 2, 3 count as zero, so role 0 has no
+        // work at all and role 1 only filters c2q(bands 1, 4) with the band-pass filter; the row pass reads y2 only
+        if (HH && ROLE == 0) return;
         const int qb = quad_base(a, by, p);
         const bool emit = p > 0;
         const float ga0 = a.gain[ROLE == 0 ? 0 : 2], ga1 = a.gain[ROLE == 0 ? 5 : 3];
@@ -235,10 +245,10 @@ struct InvS1 {
             F2 at, ab, bt, bb;         // image A (filtered with g0) and image B (g1): top / bottom real rows
             if (ROLE == 0) {
                 at = cur.v[0]; ab = cur.v[1];
-                if (HH) { at = zero2(); ab = zero2(); }
                 c2q_rows(cur.v[2], cur.v[3], ga0, ga1, bt, bb);
             } else {
-                c2q_rows(cur.v[0], cur.v[1], ga0, ga1, at, ab);
+                if (HH) { at = zero2(); ab = zero2(); }
+                else c2q_rows(cur.v[0], cur.v[1], ga0, ga1, at, ab);
                 c2q_rows(cur.v[2], cur.v[3], gb0, gb1, bt, bb);
             }
             if (EDGE) {
@@ -255,16 +265,16 @@ struct InvS1 {
                 th.acc[pmod(2 * u - CQ, RING)].x = at.x + bt.y; th.acc[pmod(2 * u - CQ, RING)].y = at.y + bt.x;
                 th.acc[pmod(2 * u + 1 - CQ, RING)].x = ab.x + bb.y; th.acc[pmod(2 * u + 1 - CQ, RING)].y = ab.y + bb.x;
             } else {
-                ring_scatter<T0, K0, M0, C0, true, RING>(2 * u, at, a.g0, th.acc);
-                ring_scatter<T1, K1, M1, C1, false, RING>(2 * u, bt, a.g1, th.acc);
+                if (!HH) ring_scatter<T0, K0, M0, C0, true, RING>(2 * u, at, a.g0, th.acc);
+                ring_scatter<T1, K1, M1, C1, HH, RING>(2 * u, bt, a.g1, th.acc);         // HH: the first touch of a ring row is its own
             }
             if (emit) {                // rows 2u and 2u+1 of this period's block are complete
                 *reinterpret_cast<F2*>(y + (2 * u) * CYP) = th.acc[pmod(2 * u - CQ, RING)];
                 *reinterpret_cast<F2*>(y + (2 * u + 1) * CYP) = th.acc[pmod(2 * u + 1 - CQ, RING)];
             }
             if (DBG != 1) {
-                ring_scatter<T0, K0, M0, C0, true, RING>(2 * u + 1, ab, a.g0, th.acc);
-                ring_scatter<T1, K1, M1, C1, false, RING>(2 * u + 1, bb, a.g1, th.acc);
+                if (!HH) ring_scatter<T0, K0, M0, C0, true, RING>(2 * u + 1, ab, a.g0, th.acc);
+                ring_scatter<T1, K1, M1, C1, HH, RING>(2 * u + 1, bb, a.g1, th.acc);
             }
         }
     }
@@ -307,9 +317,11 @@ struct InvS1 {
                 acc[0].x = p.x + r.x; acc[0].y = p.y + r.y; acc[1].x = p.z + r.z; acc[1].y = p.w + r.w;
                 acc[2].x = q.x + t.x; acc[2].y = q.y + t.y; acc[3].x = q.z + t.z; acc[3].y = q.w + t.w;
             } else {
+                if (!HH) {
 #pragma unroll
-                for (int c = 0; c < (WE0 - WS0) / 4; ++c)
-                    pair_gather4<K0, M0, C0, WS0 - CQ, 8, WE0 - WS0>(4 * c, s1[c], a.p0, acc);
+                    for (int c = 0; c < (WE0 - WS0) / 4; ++c)
+                        pair_gather4<K0, M0, C0, WS0 - CQ, 8, WE0 - WS0>(4 * c, s1[c], a.p0, acc);
+                }
 #pragma unroll
                 for (int c = 0; c < (WE1 - WS1) / 4; ++c)
                     pair_gather4<K1, M1, C1, WS1 - CQ, 8, WE1 - WS1>(4 * c, s2[c], a.p1, acc);
