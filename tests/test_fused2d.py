@@ -363,3 +363,40 @@ def test_row_pair_inverse_qshift_matches(backend, monkeypatch, variant):
     W1 = npy(x3.inverse(p3))
     monkeypatch.delenv("DTCWT_B200_INVQ_VARIANT")
     assert np.abs(W0 - W1).max() < 2e-6 * np.abs(W0).max() and np.abs(W1 - V[0]).max() < 1e-5
+
+
+@pytest.mark.parametrize("switch", ["DTCWT_B200_INVQ_ASYNC=4", "DTCWT_B200_INVQ_ASYNC=2", "DTCWT_B200_INV_ASYNC=0", "DTCWT_B200_INV_ASYNC=4",
+                                    "DTCWT_B200_Z3_SPLIT=1", "DTCWT_B200_Z3_ASYNC=0", "DTCWT_B200_Z3_ASYNC=3", "DTCWT_B200_AXIS_NG=8",
+                                    "DTCWT_B200_FWD_PREFETCH=0", "DTCWT_B200_FWD_PREFETCH=100", "DTCWT_B200_FWDQ_VARIANT=4",
+                                    "DTCWT_B200_FWDQ_VARIANT=5"])
+def test_experiment_switches_agree_with_the_defaults(backend, monkeypatch, switch):
+    """Every kernel variant that stays selectable by an environment switch (the measured-slower experiments of
+    profiles/r3_01_experiments.md and the former defaults) gives the default kernels' results to rounding: a 2-D
+    forward + inverse with gains and a cropped level, a 3-D forward + inverse, and a 3-D transform without level-1
+    highpasses on a volume whose depth takes the long-axis pass."""
+    rs = np.random.RandomState(53)
+    X = rs.rand(2, 130, 200).astype(np.float32)
+    gain = rs.rand(6, 2)
+    V = rs.rand(32, 40, 48).astype(np.float32)
+    W = rs.rand(128, 32, 40).astype(np.float32)
+    x2 = dtcwt_b200.Transform2d("near_sym_b", "qshift_b")
+    x3 = dtcwt_b200.Transform3d("near_sym_b", "qshift_b")
+
+    def run():
+        p = x2.forward_channels(X, "nhw", 2)
+        out = [npy(p.lowpass_t)] + [npy(h) for h in p.highpasses_t] + [npy(x2.inverse_channels(p, "nhw", gain))]
+        p3 = x3.forward(V, 2)
+        out += [npy(p3.lowpass)] + [npy(h) for h in p3.highpasses] + [npy(x3.inverse(p3))]
+        p4 = x3.forward(W, 2, discard_level_1=True)
+        out += [npy(p4.lowpass), npy(p4.highpasses[1]), npy(x3.inverse(p4))]
+        return out
+
+    ref = run()
+    name, value = switch.split("=")
+    monkeypatch.setenv(name, value)
+    got = run()
+    monkeypatch.delenv(name)
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert a.shape == b.shape
+        assert np.abs(a - b).max() <= 3e-6 * max(np.abs(b).max(), 1e-30)
