@@ -317,7 +317,8 @@ static int launch_fwd2d(typename K::Args& a, void* stream) {
         if (K::tiles_r(a) > 65535 || a.n > 65535) return DTCWT_B200_EUNSUPPORTED;      // grid.y / grid.z limits
         // L2 prefetch distance in percent of a resident wave of CTAs (DTCWT_B200_FWD_PREFETCH, 0: off).  Measured on the level-1
         // forward, 16 x 4096^2: off 1.021 ms, 50 % 0.991, 100 % 0.995, 200 % 1.026 (profiles/r3_01)
-        static const int pf = []() { const char* e = getenv("DTCWT_B200_FWD_PREFETCH"); return e ? atoi(e) : 50; }();
+        const char* pfe = getenv("DTCWT_B200_FWD_PREFETCH");           // read per call, like the other experiment switches
+        const int pf = pfe ? atoi(pfe) : 50;
         a.prefetch = (a.use_tma && ntiles <= 0x3fffffff) ? (int)((int64_t)sms * (per_sm > 0 ? per_sm : 1) * pf / 100) : 0;
         const dim3 grid((unsigned)K::tiles_c(a), (unsigned)K::tiles_r(a), (unsigned)a.n);
         fwd2d_kernel<K><<<grid, kFusedThreads, smem, (cudaStream_t)stream>>>(a, map);
