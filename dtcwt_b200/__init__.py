@@ -19,7 +19,7 @@ from .transform1d import Transform1d
 from .transform2d import Transform2d
 from .transform3d import Transform3d
 from .backend import register, BACKEND_NAME
-from . import coeffs, compat, keypoint, lowlevel, registration, sampling
+from . import coeffs, compat, graph, keypoint, lowlevel, registration, sampling
 from .compat import (dtwavexfm, dtwaveifm, dtwavexfm2, dtwaveifm2, dtwavexfm2b, dtwaveifm2b, dtwavexfm3, dtwaveifm3)
 from .coeffs import biort, qshift
 from .lowlevel import colfilter, coldfilt, colifilt
@@ -27,5 +27,5 @@ from .lowlevel import colfilter, coldfilt, colifilt
 __version__ = "0.1.0"
 
 __all__ = ["Pyramid", "Transform1d", "Transform2d", "Transform3d", "register", "BACKEND_NAME",
-           "coeffs", "compat", "keypoint", "lowlevel", "registration", "sampling", "dtwavexfm", "dtwaveifm", "dtwavexfm2", "dtwaveifm2",
+           "coeffs", "compat", "graph", "keypoint", "lowlevel", "registration", "sampling", "dtwavexfm", "dtwaveifm", "dtwavexfm2", "dtwaveifm2",
            "dtwavexfm2b", "dtwaveifm2b", "dtwavexfm3", "dtwaveifm3", "biort", "qshift", "colfilter", "coldfilt", "colifilt"]

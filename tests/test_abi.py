@@ -69,3 +69,12 @@ def test_package_does_not_import_oracle():
                 assert "dtcwt_oracle" not in src and "refshim" not in src, f
                 if f.endswith(".py"):      # the CPU seam lives in tests/ only (the kernel bodies keep their DTCWT_EMU build)
                     assert "emu_seam" not in src and "emulator" not in src.lower(), f
+
+
+def test_graph_helper_needs_a_cuda_tensor():
+    """dtcwt_b200.graph.Graphed is CUDA-graph capture: a host tensor is refused up front (no CPU path to fall back to)."""
+    import pytest
+    import torch
+    import dtcwt_b200
+    with pytest.raises(ValueError):
+        dtcwt_b200.graph.Graphed(lambda x: x, torch.zeros(4, 4))

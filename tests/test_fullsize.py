@@ -114,3 +114,33 @@ def test_config4_256cube_vs_reference():
         assert p.highpasses[l].shape == w.shape
         assert np.abs(p.highpasses[l] - w).max() / np.abs(w).max() < TOL
     assert np.abs(Z.cpu().numpy() - Zw).max() / np.abs(Zw).max() < 2 * TOL
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replay_matches_eager():
+    """dtcwt_b200.graph.Graphed: a forward + inverse captured in a CUDA graph replays to the eager results, for new
+    inputs of the captured shape, in 2-D (pyramid outputs) and 3-D; a wrong shape is refused."""
+    import dtcwt_b200
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    xf = dtcwt_b200.Transform2d("near_sym_b", "qshift_b")
+    X = torch.rand((512, 512), device="cuda", generator=g)
+    fwd = dtcwt_b200.graph.Graphed(lambda x: xf.forward(x, 4), X)
+    rt = dtcwt_b200.graph.Graphed(lambda x: xf.inverse(xf.forward(x, 4)), X)
+    for _ in range(3):
+        Y = torch.rand((512, 512), device="cuda", generator=g)
+        p_e = xf.forward(Y, 4)
+        p_g = fwd(Y)
+        assert torch.equal(p_g.lowpass_t, p_e.lowpass_t)
+        for a, b in zip(p_g.highpasses_t, p_e.highpasses_t):
+            assert torch.equal(a, b)
+        Z = rt(Y)
+        assert torch.equal(Z, xf.inverse(p_e))
+        assert float((Z - Y).abs().max()) < 1e-5
+    x3 = dtcwt_b200.Transform3d("near_sym_b", "qshift_b")
+    V = torch.rand((64, 64, 64), device="cuda", generator=g)
+    rt3 = dtcwt_b200.graph.Graphed(lambda v: x3.inverse(x3.forward(v, 2)), V)
+    V2 = torch.rand((64, 64, 64), device="cuda", generator=g)
+    assert torch.equal(rt3(V2), x3.inverse(x3.forward(V2, 2)))
+    with pytest.raises(ValueError):
+        rt(torch.rand((256, 512), device="cuda"))
