@@ -68,8 +68,13 @@ def complex_dtype(real_dtype):
     return _COMPLEX[real_dtype]
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)      # the handle without building a Stream object
+
+
 def _stream(t):
     if t.device.type == "cuda":
+        if _raw_stream is not None:
+            return ctypes.c_void_p(_raw_stream(t.device.index if t.device.index is not None else torch.cuda.current_device()))
         return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
     return ctypes.c_void_p(0)
 
@@ -118,7 +123,12 @@ def scratch(tag, shape, dtype, device):
     level, LoLo intermediates of a 2-D forward without include_scale): one buffer per (purpose, shape, stream), so a
     steady-state loop of transforms allocates nothing.  Work on one stream is ordered, so reusing the buffer in the next
     call on that stream is safe; another stream gets its own."""
-    stream = torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0
+    if device.type != "cuda":
+        stream = 0
+    elif _raw_stream is not None:
+        stream = _raw_stream(device.index if device.index is not None else torch.cuda.current_device())
+    else:
+        stream = torch.cuda.current_stream(device).cuda_stream
     key = (tag, tuple(int(s) for s in shape), dtype, str(device), stream)
     t = _SCRATCH.get(key)
     if t is None:

@@ -282,10 +282,24 @@ static bool tma_disabled_by_env() {
     return off;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel instance and device instead of once per launch (the
+// attribute is sticky; a small transform is bound by exactly this kind of host work).  TAG makes one flag set per call site.
+template <class TAG>
+static cudaError_t smem_opt_in(const void* kernel, size_t smem) {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    return e;
+}
+
 template <class K>
 static int launch_fwd2d(typename K::Args& a, void* stream) {
     const size_t smem = (size_t)K::kSmemFloats * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(fwd2d_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = smem_opt_in<K>((const void*)fwd2d_kernel<K>, smem);
     if (e != cudaSuccess) return (int)e;
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
@@ -310,9 +324,17 @@ static int launch_fwd2d(typename K::Args& a, void* stream) {
     if (ntiles > 0x7fffffffLL) return DTCWT_B200_EUNSUPPORTED;
     int dev = 0, sms = 0, per_sm = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
-    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fwd2d_kernel<K>, kFusedThreads, smem)) != cudaSuccess)
-        return (int)e;
+    {
+        static int c_sms[64] = {}, c_per_sm[64] = {};         // per kernel instance and device: asked once
+        if (dev >= 0 && dev < 64 && c_sms[dev] > 0) {
+            sms = c_sms[dev]; per_sm = c_per_sm[dev];
+        } else {
+            if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fwd2d_kernel<K>, kFusedThreads, smem)) != cudaSuccess)
+                return (int)e;
+            if (dev >= 0 && dev < 64) { c_per_sm[dev] = per_sm; c_sms[dev] = sms; }
+        }
+    }
     if (!K::kPersistent) {
         if (K::tiles_r(a) > 65535 || a.n > 65535) return DTCWT_B200_EUNSUPPORTED;      // grid.y / grid.z limits
         // L2 prefetch distance in percent of a resident wave of CTAs (DTCWT_B200_FWD_PREFETCH, 0: off).  Measured on the level-1
@@ -333,7 +355,7 @@ static int launch_fwd2d(typename K::Args& a, void* stream) {
 template <class K>
 static int launch_inv2d(typename K::Args& a, void* stream) {
     const size_t smem = (size_t)K::kSmemFloats * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(inv2d_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = smem_opt_in<K>((const void*)inv2d_kernel<K>, smem);
     if (e != cudaSuccess) return (int)e;
     if (a.n == 0) return DTCWT_B200_OK;
     if (K::tiles_r(a) > 65535 || a.n > 65535) return DTCWT_B200_EUNSUPPORTED;      // grid.y / grid.z limits
@@ -345,7 +367,7 @@ static int launch_inv2d(typename K::Args& a, void* stream) {
 template <class K>
 static int launch_fwds1(typename K::Args& a, void* stream) {
     const size_t smem = (size_t)K::kSmemFloats * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(fwds1_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = smem_opt_in<K>((const void*)fwds1_kernel<K>, smem);
     if (e != cudaSuccess) return (int)e;
     CUtensorMap box;
     memset(&box, 0, sizeof(box));
@@ -371,7 +393,7 @@ static int launch_fwds1(typename K::Args& a, void* stream) {
 template <class K>
 static int launch_invs1t(typename K::Args& a, void* stream) {
     const size_t smem = (size_t)K::kSmemFloats * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(invs1t_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = smem_opt_in<K>((const void*)invs1t_kernel<K>, smem);
     if (e != cudaSuccess) return (int)e;
     if (a.n == 0) return DTCWT_B200_OK;
     if (K::tiles_r(a) > 65535 || a.n > 65535) return DTCWT_B200_EUNSUPPORTED;      // grid.y / grid.z limits
@@ -383,7 +405,7 @@ static int launch_invs1t(typename K::Args& a, void* stream) {
 template <class K>
 static int launch_invs1(typename K::Args& a, void* stream) {
     const size_t smem = (size_t)K::kSmemFloats * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(invs1_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = smem_opt_in<K>((const void*)invs1_kernel<K>, smem);
     if (e != cudaSuccess) return (int)e;
     if (a.n == 0) return DTCWT_B200_OK;
     if (K::tiles_r(a) > 65535 || a.n > 65535) return DTCWT_B200_EUNSUPPORTED;      // grid.y / grid.z limits
