@@ -112,6 +112,7 @@ typedef InvS1<19, 19, 0x7ffffu, 0x7ffffu, 24, 3> InvL1_19_19;       // any odd p
 // the same with the prefetched quad rows staged in shared memory by per-thread cp.async (last argument: stages)
 typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 2, 0, false, 6> InvL1_nsbA;
 typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 2, 0, false, 4> InvL1_nsbA4;
+typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 2, 0, false, 6, true> InvL1_nsbAU;   // one instruction stream for both roles
 typedef InvS1<19, 13, kMask19, kMask13, 24, 3, BakedTaps<NearSymB_g0>, BakedTaps<NearSymB_g1>, 3, 0, false, 3> InvL1_nsbA3;   // 3 CTAs per SM
 typedef InvS1<19, 19, 0x7ffffu, 0x7ffffu, 24, 3, ArgTaps, ArgTaps, 2, 0, false, 6> InvL1_19_19A;
 typedef InvS1<7, 5, 0x7fu, 0x1fu, 8, 2, ArgTaps, ArgTaps, 2, 0, false, 4> InvL1_7_5A;
@@ -492,6 +493,7 @@ int dtcwt_b200_inv2d_level1_f32(const float* z, const float* yh, float* out, int
     }
     if (nasync > 0 && K1 == 13 && BakedTaps<NearSymB_g0>::same(a.g0) && BakedTaps<NearSymB_g1>::same(a.g1)) {
         a.periods = choose_periods(a.rows, InvL1_nsbA::RING, (int64_t)InvL1_nsbA::tiles_c(a) * a.n);
+        if (env_int("DTCWT_B200_INV_UNI", 1)) return launch_invs1<InvL1_nsbAU>(a, stream);
         if (nasync == 4) return launch_invs1<InvL1_nsbA4>(a, stream);
         if (nasync == 3) return launch_invs1<InvL1_nsbA3>(a, stream);
         return launch_invs1<InvL1_nsbA>(a, stream);

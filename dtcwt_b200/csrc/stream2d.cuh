@@ -89,8 +89,11 @@ struct InvS1Args {
 // ASYNC > 0: the prefetched quad rows live in a thread-private slice of shared memory filled by cp.async (ASYNC stages of
 // four 8-byte copies per thread) instead of NST register stages: deeper prefetch at a lower register count, and still no
 // barrier -- a thread only ever waits on its own copy groups (fused2d.cuh: async_copy8 / async_wait).
+// UNI: both roles run ONE instruction stream (the role is a warp-uniform run-time value: role 0 discards a c2q it does not
+// need) instead of two specialised copies of the unrolled period -- 19 KB of hot code instead of 38 KB, inside the 32 KB
+// L1.5 instruction cache (the two-copy form showed 11 % `no_instruction` stalls, profiles/r3_02).
 template <int K0, int K1, uint32_t M0, uint32_t M1, int RING_, int NST_, class T0 = ArgTaps, class T1 = ArgTaps, int MINB_ = 2, int DBG = 0,
-          bool HH = false, int ASYNC_ = 0>
+          bool HH = false, int ASYNC_ = 0, bool UNI_ = false>
 struct InvS1 {
     typedef InvS1Args Args;
     static constexpr int ASYNC = ASYNC_;
@@ -222,16 +225,18 @@ struct InvS1 {
         if (fr) { const F2 t = top; top = bot; bot = t; }
     }
 
+    // ROLE 0 / 1: specialised copies; ROLE 2 (UNI): one copy, `role` decides at run time (uniform within a warp)
     template <int ROLE, bool EDGE>
-    static DTCWT_D void cols_role(const Args& a, Thread& th, float* sm, int by, int p, int qc, bool cedge) {
+    static DTCWT_D void cols_role(const Args& a, Thread& th, float* sm, int by, int p, int qc, bool cedge, int role = ROLE) {
+        const bool r0 = (ROLE == 2) ? (role == 0) : (ROLE == 0);
         // HH (the band-pass launch of a `_bp` level): the lowpass and the sub-bands 0, 5, 2, 3 count as zero, so role 0 has no
         // work at all and role 1 only filters c2q(bands 1, 4) with the band-pass filter; the row pass reads y2 only
-        if (HH && ROLE == 0) return;
+        if (HH && r0) return;
         const int qb = quad_base(a, by, p);
         const bool emit = p > 0;
-        const float ga0 = a.gain[ROLE == 0 ? 0 : 2], ga1 = a.gain[ROLE == 0 ? 5 : 3];
-        const float gb0 = a.gain[1], gb1 = a.gain[4];
-        float* y = sm + ROLE * (RING * CYP) + 2 * qc;
+        const float ga0 = a.gain[r0 ? 0 : 2], ga1 = a.gain[r0 ? 5 : 3];
+        const float gb0 = (ROLE == 2 && r0) ? a.gain[0] : a.gain[1], gb1 = (ROLE == 2 && r0) ? a.gain[5] : a.gain[4];
+        float* y = sm + (r0 ? 0 : 1) * (RING * CYP) + 2 * qc;
 #pragma unroll
         for (int u = 0; u < PER; ++u) {
             Raw cur;
@@ -243,7 +248,14 @@ struct InvS1 {
                 load_stage<EDGE>(a, th, th.st[(ASYNC_ > 0 ? 0 : u % NST)], qb + u + NST);
             }
             F2 at, ab, bt, bb;         // image A (filtered with g0) and image B (g1): top / bottom real rows
-            if (ROLE == 0) {
+            if (ROLE == 2) {
+                // one stream for both roles: role 1 needs c2q(bands 2, 3) for A, role 0 takes the two lowpass rows as they are
+                F2 ct, cb;
+                c2q_rows(cur.v[0], cur.v[1], a.gain[2], a.gain[3], ct, cb);
+                at = r0 ? cur.v[0] : ct; ab = r0 ? cur.v[1] : cb;
+                if (HH) { at = zero2(); ab = zero2(); }
+                c2q_rows(cur.v[2], cur.v[3], gb0, gb1, bt, bb);
+            } else if (ROLE == 0) {
                 at = cur.v[0]; ab = cur.v[1];
                 c2q_rows(cur.v[2], cur.v[3], ga0, ga1, bt, bb);
             } else {
@@ -283,7 +295,10 @@ struct InvS1 {
     static DTCWT_D void cols(const Args& a, Thread& th, float* sm, int bx, int by, int bz, int tid, int p) {
         const int qc = tid % QC, role = tid / QC;                // role is uniform within a warp
         const bool edge = edge_period(a, bx, by, p), cedge = col_edge(a, bx);
-        if (role == 0) {
+        if (UNI_) {
+            if (edge) cols_role<2, true>(a, th, sm, by, p, qc, cedge, role);
+            else cols_role<2, false>(a, th, sm, by, p, qc, cedge, role);
+        } else if (role == 0) {
             if (edge) cols_role<0, true>(a, th, sm, by, p, qc, cedge);
             else cols_role<0, false>(a, th, sm, by, p, qc, cedge);
         } else {

@@ -368,7 +368,7 @@ def test_row_pair_inverse_qshift_matches(backend, monkeypatch, variant):
 @pytest.mark.parametrize("switch", ["DTCWT_B200_INVQ_ASYNC=4", "DTCWT_B200_INVQ_ASYNC=2", "DTCWT_B200_INV_ASYNC=0", "DTCWT_B200_INV_ASYNC=4",
                                     "DTCWT_B200_Z3_SPLIT=1", "DTCWT_B200_Z3_ASYNC=0", "DTCWT_B200_Z3_ASYNC=3", "DTCWT_B200_AXIS_NG=8",
                                     "DTCWT_B200_FWD_PREFETCH=0", "DTCWT_B200_FWD_PREFETCH=100", "DTCWT_B200_FWDQ_VARIANT=4",
-                                    "DTCWT_B200_FWDQ_VARIANT=5"])
+                                    "DTCWT_B200_FWDQ_VARIANT=5", "DTCWT_B200_INV_UNI=0"])
 def test_experiment_switches_agree_with_the_defaults(backend, monkeypatch, switch):
     """Every kernel variant that stays selectable by an environment switch (the measured-slower experiments of
     profiles/r3_01_experiments.md and the former defaults) gives the default kernels' results to rounding: a 2-D
